@@ -1,0 +1,303 @@
+"""Model-parallel Fourier Neural Operator -- portable (torch.fft / torch.distributed) backend.
+
+This backend defines the *semantics* of the framework: any device, fp32/fp64 (bf16 is
+up-cast inside the transforms), any Cartesian partition, gloo or NCCL.  On B200 the fused
+sm_100a engine (:mod:`dfno_b200.models.fused`) computes the same function; run over NCCL,
+this backend is also the measured baseline (``bench.py --impl baseline``).
+
+Mathematical specification of one block (reference
+``/root/reference/dfno/dfno.py:241-291``)::
+
+    y0  = W_lin ._c x                                          (no bias)
+    X^  = Trunc( FFT_{axes 1..n-1}( RFFT_{axis n}(x) ) )       keep [0,m) u [N-m,N), rfft axis [0,m)
+    Y^[b,o,k] = sum_i X^[b,i,k] R[i,o,k]
+    y   = IRFFT_n( IFFT_{1..n-1}( ZeroPad(Y^) ) )
+    out = gelu_erf(y0 + y)
+
+with the field block-decomposed over ``P_x`` and the transform done in two local stages
+(``P_m`` then ``P_y``, see :mod:`dfno_b200.parallel.planner`) joined by four Repartitions.
+Spectral weights are sharded by Fourier mode over ``P_y`` and stored as one parameter per
+non-empty low/high "corner" -- the reference's checkpoint layout.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..parallel.decomposition import shard_bounds
+from ..parallel.partition import Partition
+from ..parallel.planner import (corner_boxes, make_pencil_plan, spectrum_shape, validate_modes)
+from ..parallel.primitives import Repartition
+from ..utils.misc import alphabet
+from ..utils.timers import CommTimer
+from .linear import BroadcastedLinear
+from .norm import DistributedBatchNorm
+
+__all__ = ["DistributedFNOBlock", "DistributedFNO", "DistributedFNONd", "infer_global_shape"]
+
+
+def _complex_of(dtype: torch.dtype) -> torch.dtype:
+    return torch.complex128 if dtype == torch.float64 else torch.complex64
+
+
+def _keep_modes(x: torch.Tensor, dim: int, m: int, two_sided: bool) -> torch.Tensor:
+    """Truncate a spectrum axis to its retained modes."""
+    if not two_sided:
+        return x.narrow(dim, 0, m)
+    n = x.shape[dim]
+    return torch.cat((x.narrow(dim, 0, m), x.narrow(dim, n - m, m)), dim=dim)
+
+
+def _pad_modes(y: torch.Tensor, dim: int, m: int, n_full: int, two_sided: bool) -> torch.Tensor:
+    """Inverse of :func:`_keep_modes`: scatter retained modes into a zero spectrum."""
+    if y.shape[dim] == n_full:
+        return y
+    shape = list(y.shape)
+    shape[dim] = n_full
+    out = y.new_zeros(shape)
+    out.narrow(dim, 0, m).copy_(y.narrow(dim, 0, m))
+    if two_sided:
+        out.narrow(dim, n_full - m, m).copy_(y.narrow(dim, m, m))
+    return out
+
+
+class DistributedFNOBlock(nn.Module):
+    """One Fourier layer on a ``P_x``-decomposed field.
+
+    ``in_shape`` is the **global** ``[B, width, *spatial, T]``; ``modes`` has one entry per
+    transformed axis (last = time / rfft axis).
+    """
+
+    def __init__(self, P_x: Partition, in_shape: Sequence[int], modes: Sequence[int],
+                 device=torch.device("cpu"), dtype=torch.float32, plan: str = "reference"):
+        super().__init__()
+        self.P_x = P_x
+        self.in_shape = [int(s) for s in in_shape]
+        self.modes = [int(m) for m in modes]
+        self.width = self.in_shape[1]
+        self.n = P_x.dim - 2
+        self.device, self.dtype = device, dtype
+        self.compute_dtype = torch.float32 if dtype in (torch.bfloat16, torch.float16) else dtype
+        self.dtype_complex = _complex_of(self.compute_dtype)
+        validate_modes(self.in_shape, self.modes)
+
+        # ---- pencil plan and the four re-shards
+        self.fft_shape = spectrum_shape(self.in_shape, self.modes)
+        self.plan = make_pencil_plan(P_x.shape, kind=plan, spectrum=self.fft_shape)
+        self.dim_m = np.asarray(self.plan.dim_m)
+        self.dim_y = np.asarray(self.plan.dim_y)
+        self.P_m = P_x.create_cartesian_topology_partition(self.plan.grid_m)
+        self.P_y = P_x.create_cartesian_topology_partition(self.plan.grid_y)
+
+        # global shapes at the two re-shard points: full field, and spectrum after stage m
+        shape_after_m = list(self.in_shape)
+        for d in self.plan.dim_m:
+            shape_after_m[d] = self.fft_shape[d]
+        cdt = self.dtype_complex
+        self.R1 = Repartition(P_x, self.P_m, self.in_shape, dtype=self.compute_dtype)
+        self.R2 = Repartition(self.P_m, self.P_y, shape_after_m, dtype=cdt)
+        self.R3 = Repartition(self.P_y, self.P_m, shape_after_m, dtype=cdt)
+        self.R4 = Repartition(self.P_m, P_x, self.in_shape, dtype=self.compute_dtype)
+
+        # ---- mode-restriction tables (API parity: dim -> retained count)
+        rfft_dim = self.plan.rfft_dim
+        self.restrict_prefixes = {int(d): self.modes[d - 2] for d in (*self.plan.dim_m, *self.plan.dim_y)}
+        self.restrict_suffixes = {int(d): self.modes[d - 2] for d in (*self.plan.dim_m, *self.plan.dim_y)
+                                  if d != rfft_dim}
+
+        # ---- spectral weights: one parameter per non-empty corner of the local P_y slab
+        self.scale = 1.0 / (self.width * self.width)
+        self.weights = nn.ParameterList()
+        self.slices: List[tuple] = []
+        if self.P_y.active:
+            start, stop = shard_bounds(self.fft_shape, self.P_y.shape, self.P_y.index)
+            for box in corner_boxes(self.fft_shape, self.modes, start, stop):
+                ext = [b - a for a, b in box]
+                w = self.scale * torch.rand(self.width, self.width, *ext, device=device, dtype=cdt)
+                self.weights.append(nn.Parameter(w))
+                self.slices.append((slice(None), slice(None)) + tuple(slice(a, b) for a, b in box))
+
+        letters = alphabet(P_x.dim, as_array=True)
+        xs, ws, ys = list(letters), list(letters), list(letters)
+        xs[1], ws[0], ws[1], ys[1] = "i", "i", "o", "o"
+        self.eqn = f"{''.join(xs)},{''.join(ws)}->{''.join(ys)}"
+
+        self.linear = BroadcastedLinear(P_x, self.width, self.width, dim=1, bias=False,
+                                        device=device, dtype=dtype)
+        self.timer = CommTimer()
+        self.dt_comm = 0.0
+
+    # ------------------------------------------------------------------ API-parity helpers
+    def restrict(self, x: torch.Tensor, dim: int) -> torch.Tensor:
+        """Discard the unused high-frequency entries along ``dim``."""
+        if dim not in self.restrict_prefixes:
+            return x
+        return _keep_modes(x, dim, self.restrict_prefixes[dim], dim in self.restrict_suffixes)
+
+    def zeropad(self, y: torch.Tensor, dim: int, target_shape: Sequence[int]) -> torch.Tensor:
+        """Re-insert zeros for the discarded entries along ``dim``."""
+        if dim not in self.restrict_prefixes:
+            return y
+        return _pad_modes(y, dim, self.restrict_prefixes[dim], int(target_shape[dim]),
+                          dim in self.restrict_suffixes)
+
+    # ------------------------------------------------------------------ spectral path
+    def spectral_forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``x`` (P_x shard, real) -> spectral branch output (P_x shard, real)."""
+        t = self.timer
+        rdim = self.plan.rfft_dim
+        full = {}
+        with t:
+            x = self.R1(x)
+        if self.P_m.active:
+            full[rdim] = x.shape[rdim]
+            x = _keep_modes(torch.fft.rfft(x, dim=rdim), rdim, self.modes[rdim - 2], False)
+            for d in reversed(self.plan.dim_m[:-1]):
+                full[d] = x.shape[d]
+                x = _keep_modes(torch.fft.fft(x, dim=d), d, self.modes[d - 2], True)
+        with t:
+            x = self.R2(x)
+        if self.P_y.active:
+            for d in reversed(self.plan.dim_y):
+                full[d] = x.shape[d]
+                x = _keep_modes(torch.fft.fft(x, dim=d), d, self.modes[d - 2], True)
+            y = torch.empty_like(x)
+            for w, sl in zip(self.weights, self.slices):
+                y[sl] = torch.einsum(self.eqn, x[sl], w)
+            for d in self.plan.dim_y:
+                y = torch.fft.ifft(_pad_modes(y, d, self.modes[d - 2], full[d], True), dim=d)
+        else:
+            y = x
+        with t:
+            y = self.R3(y)
+        if self.P_m.active:
+            for d in self.plan.dim_m[:-1]:
+                y = torch.fft.ifft(_pad_modes(y, d, self.modes[d - 2], full[d], True), dim=d)
+            y = torch.fft.irfft(y, n=full[rdim], dim=rdim)
+        with t:
+            y = self.R4(y)
+        return y
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.timer.reset()
+        y0 = self.linear(x)
+        y = self.spectral_forward(x.to(self.compute_dtype))
+        self.dt_comm = self.timer.seconds + self.linear.dt_comm
+        return F.gelu(y0 + y.to(y0.dtype))
+
+
+class DistributedFNO(nn.Module):
+    """Lift (time axis ``T_in->T_out``, channels ``C_in->width``), ``num_blocks`` Fourier
+    layers, projection ``width->128->1``.  ``in_shape`` is the **global**
+    ``[B, C_in, *spatial, T_in]``; the forward takes/returns this rank's ``P_x`` shard
+    (``/root/reference/dfno/dfno.py:293-353``).
+
+    ``backend="auto"`` hands construction to the fused sm_100a engine when the device,
+    dtype and partition are ones it covers (see :func:`dfno_b200.models.fused.supports`);
+    ``backend="torch"`` forces this portable implementation.
+    """
+
+    def __new__(cls, *args, backend: str = "auto", **kwargs):
+        if cls is DistributedFNO and backend != "torch":
+            from . import fused
+            if fused.wants(args, kwargs, backend):
+                return fused.FusedDistributedFNO(*args, **kwargs)
+        return super().__new__(cls)
+
+    def __init__(self, P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
+                 modes: Sequence[int], num_blocks: int = 4, device=torch.device("cpu"),
+                 dtype=torch.float32, plan: str = "reference", backend: str = "auto"):
+        super().__init__()
+        self.P_x = P_x
+        self.in_shape = [int(s) for s in in_shape]
+        self.out_timesteps, self.width = int(out_timesteps), int(width)
+        self.modes = [int(m) for m in modes]
+        self.num_blocks = int(num_blocks)
+        self.device, self.dtype = device, dtype
+        if len(self.in_shape) != P_x.dim:
+            raise ValueError(f"in_shape {self.in_shape} does not match partition rank {P_x.dim}")
+        if int(P_x.shape[-1]) != 1 or int(P_x.shape[1]) != 1:
+            raise NotImplementedError(
+                "the time and channel axes are contracted locally by the lift/projection; "
+                "partition the spatial (or batch) axes instead")
+
+        self.block_in_shape = [self.in_shape[0], self.width, *self.in_shape[2:-1], self.out_timesteps]
+        kw = dict(device=device, dtype=dtype)
+        self.linear1 = BroadcastedLinear(P_x, self.in_shape[-1], self.out_timesteps, dim=-1, **kw)
+        self.linear2 = BroadcastedLinear(P_x, self.in_shape[1], self.width, dim=1, **kw)
+        self.linear3 = BroadcastedLinear(P_x, self.width, 128, dim=1, **kw)
+        self.linear4 = BroadcastedLinear(P_x, 128, 1, dim=1, **kw)
+        self.blocks = nn.ModuleList(
+            DistributedFNOBlock(P_x, self.block_in_shape, self.modes, plan=plan, **kw)
+            for _ in range(self.num_blocks))
+        # constructed for state-dict parity, not part of the forward (reference :325-346)
+        self.bn1 = DistributedBatchNorm(P_x, self.width, **kw)
+        self.bn2 = DistributedBatchNorm(P_x, self.width, **kw)
+        self.dt_comm = 0.0
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dt = 0.0
+        x = F.gelu(self.linear1(x)); dt += self.linear1.dt_comm
+        x = F.gelu(self.linear2(x)); dt += self.linear2.dt_comm
+        for blk in self.blocks:
+            x = blk(x); dt += blk.dt_comm
+        x = F.gelu(self.linear3(x)); dt += self.linear3.dt_comm
+        x = self.linear4(x); dt += self.linear4.dt_comm
+        self.dt_comm = dt
+        return x
+
+
+def infer_global_shape(P: Partition, local_shape: Sequence[int]) -> List[int]:
+    """Global tensor shape from every rank's balanced shard shape (one all-gather)."""
+    import torch.distributed as dist
+    local = [int(s) for s in local_shape]
+    if P.group is None or not P.active:
+        return local
+    gathered = [None] * P.size
+    dist.all_gather_object(gathered, (P.rank, local), group=P.group)
+    by_rank = dict(gathered)
+    out = []
+    for ax in range(P.dim):
+        tot = 0
+        for i in range(int(P.shape[ax])):
+            idx = [0] * P.dim
+            idx[ax] = i
+            tot += by_rank[int(np.ravel_multi_index(idx, tuple(int(s) for s in P.shape)))][ax]
+        out.append(tot)
+    return out
+
+
+class DistributedFNONd(nn.Module):
+    """Keyword-style, lazily-shaped front end kept for scripts written against the older
+    API (``/root/reference/tests/gradient_test_dfno.py:11-26``): no ``in_shape`` -- it is
+    inferred from the first input shard.  ``decomposition_order`` and ``P_y`` are accepted
+    and ignored (the pencil plan is derived from ``P_x``)."""
+
+    def __init__(self, P_x: Partition = None, width: int = 20, modes: Sequence[int] = None,
+                 out_timesteps: int = 1, decomposition_order: int = 1, num_blocks: int = 4,
+                 device=torch.device("cpu"), dtype=torch.float32, P_y: Optional[Partition] = None,
+                 in_shape: Optional[Sequence[int]] = None, **extra):
+        super().__init__()
+        self.P_x = P_x
+        self._cfg = dict(out_timesteps=out_timesteps, width=width, modes=modes,
+                         num_blocks=num_blocks, device=device, dtype=dtype, **extra)
+        self.decomposition_order = decomposition_order
+        self.net: Optional[DistributedFNO] = None
+        if in_shape is not None:
+            self._materialise(in_shape)
+
+    def _materialise(self, in_shape) -> None:
+        self.net = DistributedFNO(self.P_x, list(in_shape), **self._cfg)
+
+    @property
+    def dt_comm(self) -> float:
+        return 0.0 if self.net is None else self.net.dt_comm
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.net is None:
+            self._materialise(infer_global_shape(self.P_x, x.shape))
+        return self.net(x)
