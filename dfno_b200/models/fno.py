@@ -31,7 +31,7 @@ import torch.nn.functional as F
 from ..parallel.decomposition import shard_bounds
 from ..parallel.partition import Partition
 from ..parallel.planner import (corner_boxes, make_pencil_plan, spectrum_shape, validate_modes)
-from ..parallel.primitives import Repartition
+from ..parallel.primitives import Repartition, replica_grad_sync
 from ..utils.misc import alphabet
 from ..utils.timers import CommTimer
 from .linear import BroadcastedLinear
@@ -63,6 +63,28 @@ def _pad_modes(y: torch.Tensor, dim: int, m: int, n_full: int, two_sided: bool) 
     if two_sided:
         out.narrow(dim, n_full - m, m).copy_(y.narrow(dim, m, m))
     return out
+
+
+def _fft(x: torch.Tensor, dim: int, kind: str, n: Optional[int] = None) -> torch.Tensor:
+    """torch.fft wrapper that tolerates zero-volume shards (a rank can own no modes when an
+    axis has fewer retained modes than workers; MKL/cuFFT reject empty batches)."""
+    if x.numel() == 0:
+        # stay attached to the autograd graph: the backward of an empty shard must still
+        # run the matching collectives on this rank
+        shape = list(x.shape)
+        tie = x.sum() * 0
+        if kind == "rfft":
+            shape[dim] = shape[dim] // 2 + 1
+            return x.new_zeros(shape, dtype=_complex_of(x.dtype)) + tie
+        if kind == "irfft":
+            shape[dim] = n
+            return x.new_zeros(shape, dtype=x.real.dtype) + tie.real
+        return x
+    if kind == "rfft":
+        return torch.fft.rfft(x, dim=dim)
+    if kind == "irfft":
+        return torch.fft.irfft(x, n=n, dim=dim)
+    return torch.fft.fft(x, dim=dim) if kind == "fft" else torch.fft.ifft(x, dim=dim)
 
 
 class DistributedFNOBlock(nn.Module):
@@ -121,6 +143,10 @@ class DistributedFNOBlock(nn.Module):
                 self.weights.append(nn.Parameter(w))
                 self.slices.append((slice(None), slice(None)) + tuple(slice(a, b) for a, b in box))
 
+        # data-parallel replicas (batch axis of P_y partitioned) share each weight shard:
+        # their gradients are summed in the backward
+        self.replica_group, self.replica_ranks = self.P_y.axis_group([0])
+
         letters = alphabet(P_x.dim, as_array=True)
         xs, ws, ys = list(letters), list(letters), list(letters)
         xs[1], ws[0], ws[1], ys[1] = "i", "i", "o", "o"
@@ -155,29 +181,31 @@ class DistributedFNOBlock(nn.Module):
             x = self.R1(x)
         if self.P_m.active:
             full[rdim] = x.shape[rdim]
-            x = _keep_modes(torch.fft.rfft(x, dim=rdim), rdim, self.modes[rdim - 2], False)
+            x = _keep_modes(_fft(x, rdim, 'rfft'), rdim, self.modes[rdim - 2], False)
             for d in reversed(self.plan.dim_m[:-1]):
                 full[d] = x.shape[d]
-                x = _keep_modes(torch.fft.fft(x, dim=d), d, self.modes[d - 2], True)
+                x = _keep_modes(_fft(x, d, 'fft'), d, self.modes[d - 2], True)
         with t:
             x = self.R2(x)
         if self.P_y.active:
             for d in reversed(self.plan.dim_y):
                 full[d] = x.shape[d]
-                x = _keep_modes(torch.fft.fft(x, dim=d), d, self.modes[d - 2], True)
-            y = torch.empty_like(x)
+                x = _keep_modes(_fft(x, d, 'fft'), d, self.modes[d - 2], True)
+            # the corners tile the whole local slab, so every entry is written exactly once;
+            # a rank that owns no modes keeps a (differentiable) empty tensor
+            y = torch.empty_like(x) if len(self.weights) else x * 0
             for w, sl in zip(self.weights, self.slices):
-                y[sl] = torch.einsum(self.eqn, x[sl], w)
+                y[sl] = torch.einsum(self.eqn, x[sl], replica_grad_sync(w, self.replica_group))
             for d in self.plan.dim_y:
-                y = torch.fft.ifft(_pad_modes(y, d, self.modes[d - 2], full[d], True), dim=d)
+                y = _fft(_pad_modes(y, d, self.modes[d - 2], full[d], True), d, 'ifft')
         else:
             y = x
         with t:
             y = self.R3(y)
         if self.P_m.active:
             for d in self.plan.dim_m[:-1]:
-                y = torch.fft.ifft(_pad_modes(y, d, self.modes[d - 2], full[d], True), dim=d)
-            y = torch.fft.irfft(y, n=full[rdim], dim=rdim)
+                y = _fft(_pad_modes(y, d, self.modes[d - 2], full[d], True), d, 'ifft')
+            y = _fft(_pad_modes(y, rdim, self.modes[rdim - 2], full[rdim] // 2 + 1, False), rdim, 'irfft', n=full[rdim])
         with t:
             y = self.R4(y)
         return y

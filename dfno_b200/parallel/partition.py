@@ -152,6 +152,29 @@ class Partition:
         return (f"Partition(shape={tuple(int(s) for s in self.shape)}, ranks={self.world_ranks}, "
                 f"rank={self.rank}, active={self.active})")
 
+    def axis_group(self, axes: Sequence[int]):
+        """Process group of the ranks that differ from this one only along ``axes``
+        (e.g. ``axes=[0]``: the data-parallel replicas of a model shard).  Collective over
+        the world on first use: every rank walks all such rank sets in the same order.
+        Returns ``(group, world_ranks)``; group is None for singleton sets / inactive ranks."""
+        import itertools
+        axes = sorted(int(a) % self.dim for a in axes)
+        others = [d for d in range(self.dim) if d not in axes]
+        mine = (None, ())
+        for fixed in itertools.product(*[range(int(self.shape[d])) for d in others]):
+            ranks = []
+            for var in itertools.product(*[range(int(self.shape[d])) for d in axes]):
+                idx = [0] * self.dim
+                for d, v in zip(others, fixed):
+                    idx[d] = v
+                for d, v in zip(axes, var):
+                    idx[d] = v
+                ranks.append(self.world_rank_of(idx))
+            g = _group_for(ranks)
+            if self.active and world_rank() in ranks:
+                mine = (g, tuple(ranks))
+        return mine
+
     # ------------------------------------------------------------------ small collectives
     def barrier(self) -> None:
         if self.group is not None and self.active:

@@ -31,7 +31,7 @@ from .partition import Partition, _group_for, world_rank
 __all__ = [
     "zero_volume_tensor", "is_zero_volume", "Broadcast", "SumReduce", "AllSumReduce",
     "Repartition", "DistributedTranspose", "ZeroVolumeCorrectorFunction", "RepartitionPlan",
-    "build_repartition_plan",
+    "build_repartition_plan", "replica_grad_sync",
 ]
 
 
@@ -157,6 +157,27 @@ class _AllSumReduceFn(torch.autograd.Function):
         buf = _comm_view(g).clone()
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=ctx.group)
         return (torch.view_as_complex(buf) if g.is_complex() else buf), None
+
+
+class _ReplicaGradSyncFn(torch.autograd.Function):
+    """Identity in the forward; all-reduce(sum) of the gradient over the replicas that hold
+    a copy of the same parameter shard (data parallelism along the batch axis -- absent
+    from the reference)."""
+
+    @staticmethod
+    def forward(ctx, w, group):
+        ctx.group = group
+        return w.view_as(w)
+
+    @staticmethod
+    def backward(ctx, g):
+        buf = _comm_view(g).clone()
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=ctx.group)
+        return (torch.view_as_complex(buf) if g.is_complex() else buf), None
+
+
+def replica_grad_sync(w: torch.Tensor, group) -> torch.Tensor:
+    return w if group is None else _ReplicaGradSyncFn.apply(w, group)
 
 
 class Broadcast(nn.Module):

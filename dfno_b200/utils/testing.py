@@ -47,7 +47,7 @@ def _worker(rank: int, world_size: int, port: int, cuda: bool, fn: Callable, arg
         pass
 
 
-def run_distributed(fn: Callable, world_size: int, *args, cuda: bool = False, timeout: float = 600.0) -> List[Any]:
+def run_distributed(fn: Callable, world_size: int, *args, cuda: bool = False, timeout: float = 240.0) -> List[Any]:
     """Run ``fn`` on ``world_size`` spawned ranks; raises if any rank failed."""
     port = free_port()
     with tempfile.TemporaryDirectory() as outdir:

@@ -1,0 +1,146 @@
+"""Distributed FNO == serial FNO, Taylor gradient test, checkpoint round trips (gloo)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from dfno_b200.utils.testing import run_distributed
+
+
+def _make(d, P_x, cfg, plan="reference"):
+    return d.DistributedFNO(P_x, cfg["in_shape"], cfg["nt"], cfg["width"], cfg["modes"],
+                            num_blocks=cfg["blocks"], dtype=torch.float64, plan=plan, backend="torch")
+
+
+def _global_io(cfg, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(*cfg["in_shape"], dtype=torch.float64, generator=g)
+    return x
+
+
+def _serial_equiv(rank, ws, grid, cfg, plan, tmp):
+    import dfno_b200 as d
+    from dfno_b200.parallel.decomposition import shard_bounds, assemble_slices
+    _, P_x, P_0 = d.create_standard_partitions(grid)
+    P_1 = d.Partition([rank], [1] * len(grid))            # a private single-rank world
+    torch.manual_seed(7)
+    serial = _make(d, P_1, cfg)
+    state = d.gather_global_state(serial, to_all=True)
+    net = _make(d, P_x, cfg, plan)
+    d.load_global_state(net, state)
+    xg = _global_io(cfg).requires_grad_()
+    yg = serial(xg)
+    yg.square().sum().backward()
+    out = {}
+    if P_x.active:
+        lo, hi = shard_bounds(cfg["in_shape"], P_x.shape, P_x.index)
+        xl = xg.detach()[assemble_slices(lo, hi)].clone().requires_grad_()
+        yl = net(xl)
+        oshape = list(cfg["in_shape"]); oshape[1] = 1; oshape[-1] = cfg["nt"]
+        lo_o, hi_o = shard_bounds(oshape, P_x.shape, P_x.index)
+        want = yg.detach()[assemble_slices(lo_o, hi_o)]
+        out["fwd"] = float((yl.detach() - want).abs().max() / want.abs().max())
+        yl.square().sum().backward()
+        out["dx"] = float((xl.grad - xg.grad[assemble_slices(lo, hi)]).abs().max() / xg.grad.abs().max())
+        # parameter gradients: compare in canonical (global) form
+    for model in (net, serial):
+        for p in model.parameters():
+            p.data = p.grad.clone() if p.grad is not None else torch.zeros_like(p.data)
+    gd = d.gather_global_state(net, to_all=True)
+    gs = d.gather_global_state(serial, to_all=True)
+    out["dparam"] = max(float((gd[k] - gs[k]).abs().max() / gs[k].abs().max().clamp_min(1e-30))
+                        for k in gs if gs[k].is_floating_point() or gs[k].is_complex())
+    # per-rank checkpoint round trip + reshard into the serial layout
+    d.load_global_state(net, state)
+    d.save_checkpoint(net, tmp, epoch=3, extra={"plan": plan})
+    torch.distributed.barrier()
+    net2 = _make(d, P_x, cfg, plan)
+    info = d.load_checkpoint(net2, tmp, epoch=3)
+    assert info["epoch"] == 3
+    for (n1, a), (n2, b) in zip(net.state_dict().items(), net2.state_dict().items()):
+        assert n1 == n2 and torch.equal(a, b)
+    serial2 = _make(d, P_1, cfg)
+    d.reshard_checkpoint(tmp, serial2, epoch=3)
+    s2 = d.gather_global_state(serial2, to_all=True)
+    out["reshard"] = max(float((s2[k] - state[k]).abs().max()) for k in state
+                         if k.startswith(("linear", "blocks")))
+    out["nkeys"] = len(net.state_dict())
+    return out
+
+
+CFG_2D = dict(in_shape=[2, 1, 12, 10, 3], nt=8, width=5, modes=(3, 2, 3), blocks=2)
+CFG_3D = dict(in_shape=[1, 2, 8, 9, 8, 2], nt=6, width=4, modes=(2, 3, 2, 3), blocks=2)
+
+
+@pytest.mark.parametrize("ws,grid,cfg,plan", [
+    (4, (1, 1, 2, 2, 1), CFG_2D, "reference"),        # odd n: P_y leaves ranks idle
+    (4, (1, 1, 2, 2, 1, 1), CFG_3D, "reference"),
+    (4, (1, 1, 1, 4, 1, 1), CFG_3D, "reference"),     # 1 x k pencil: R1/R4 identity
+    (4, (1, 1, 1, 4, 1, 1), CFG_3D, "balanced"),
+    (2, (2, 1, 1, 1, 1), CFG_2D, "reference"),        # batch (data) parallel axis
+])
+def test_distributed_equals_serial(ws, grid, cfg, plan):
+    with tempfile.TemporaryDirectory() as tmp:
+        res = run_distributed(_serial_equiv, ws, grid, cfg, plan, tmp)
+    for r in res:
+        assert r.get("fwd", 0) < 1e-11 and r.get("dx", 0) < 1e-10, r
+        assert r["dparam"] < 1e-9 and r["reshard"] == 0.0, r
+
+
+def _taylor(rank, ws, grid, cfg, names):
+    import dfno_b200 as d
+    _, P_x, P_0 = d.create_standard_partitions(grid)
+    torch.manual_seed(11 + rank)
+    net = _make(d, P_x, cfg)
+    info = d.compute_distribution_info(P_x, cfg["in_shape"])
+    bad = []
+    for r in d.gradient_test(net, tuple(int(s) for s in info["shape"]), names=names):
+        if not r.ok:
+            bad.append(str(r))
+    return bad
+
+
+@pytest.mark.slow
+def test_taylor_gradient_2d_64x64_world2():
+    """BASELINE.json config 1: 2-D FNO 64x64, 4 layers, 12 modes, world_size=2, CPU/gloo."""
+    cfg = dict(in_shape=[1, 1, 64, 64, 4], nt=8, width=8, modes=(12, 12, 4), blocks=4)
+    names = ["linear1.W", "linear2.b", "blocks.0.weights.0", "blocks.1.weights.1", "blocks.2.linear.W",
+             "blocks.3.weights.0", "linear3.W", "linear4.W", "linear4.b"]
+    res = run_distributed(_taylor, 2, (1, 1, 2, 1, 1), cfg, names, timeout=1500)
+    assert all(not bad for bad in res), "\n".join(sum(res, []))
+
+
+def test_taylor_gradient_small_all_params_world4():
+    cfg = dict(in_shape=[1, 1, 8, 8, 2], nt=4, width=3, modes=(2, 2, 2), blocks=1)
+    res = run_distributed(_taylor, 4, (1, 1, 2, 2, 1), cfg, None)
+    assert all(not bad for bad in res), "\n".join(sum(res, []))
+
+
+def _fnond(rank, ws):
+    import dfno_b200 as d
+    _, P_x, P_0 = d.create_standard_partitions((1, 1, 2, 1, 1))
+    f = d.DistributedFNONd(P_x=P_x, width=4, modes=(2, 2, 2), out_timesteps=4, decomposition_order=1,
+                           num_blocks=1, device=torch.device("cpu"), dtype=torch.float64, P_y=P_x)
+    y = f(torch.rand(1, 1, 4, 8, 1, dtype=torch.float64))
+    crit = d.DistributedRelativeLpLoss(P_x)
+    mse = d.DistributedMSELoss(P_x)
+    t = torch.rand_like(y)
+    l1, l2 = crit(y, t), mse(y, t)
+    (l1 + l2).backward()
+    # reference values from the gathered tensors
+    G = d.Repartition(P_x, P_0)
+    yg, tg = G(y.detach()), G(t)
+    if P_0.active:
+        assert f.net.in_shape == [1, 1, 8, 8, 1]
+        want1 = (torch.linalg.vector_norm((yg - tg).reshape(1, -1), dim=1) /
+                 torch.linalg.vector_norm(tg.reshape(1, -1), dim=1)).mean()
+        assert torch.allclose(l1, want1) and torch.allclose(l2, (yg - tg).square().mean())
+    else:
+        assert float(l1) == 0.0 and float(l2) == 0.0
+    return True
+
+
+def test_lazy_fnond_and_losses():
+    assert all(run_distributed(_fnond, 2))
