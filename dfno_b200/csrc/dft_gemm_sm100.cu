@@ -1,0 +1,335 @@
+// dft_gemm_sm100.cu -- "skinny" GEMM with a resident operator matrix on tcgen05 / TMEM / TMA.
+//
+//     C[M, N] = A[M, K] * B[N, K]^T        A, B bf16 (K-major), fp32 accumulation in TMEM
+//
+// This is the workhorse of the Fourier layers: every truncated (inverse) DFT stage of
+// SURVEY.md §2.5 (K4, K5, K7, K10, K12, K13 and their adjoints) is such a product with
+// M = millions of "lines" of the field, K = the transformed axis (x interleaved re/im),
+// N = the retained modes (x re/im) -- i.e. a tiny operator B applied to a huge streamed A.
+// The design follows from that shape, not from a square-GEMM template:
+//
+//   * B (<= 256 x 256 bf16) is loaded ONCE per CTA by TMA and stays resident in shared memory.
+//   * the kernel is persistent (one CTA per SM); A tiles of 128 rows x K stream through a
+//     multi-stage TMA/mbarrier ring (SWIZZLE_128B, 64-element K blocks);
+//   * one thread issues tcgen05.mma (M=128, N=N_pad, K=16) into a double-buffered TMEM
+//     accumulator, so the epilogue of tile i overlaps the loads+MMA of tile i+1;
+//   * the epilogue (4 warps = the 4 TMEM lane quarters) reads the accumulator with
+//     tcgen05.ld and writes either a row-major tile (optionally adding a bf16 tensor) or a
+//     *scattered, transposed* layout addressed through a small mixed-radix table.  The
+//     scatter target may live on another GPU: the base pointer is selected per peer from a
+//     table of NVLink-mapped symmetric buffers, which is how the pencil-transpose
+//     all-to-all (Repartition R2/R3) is fused into the producing GEMM:
+//     the tile goes straight from TMEM to its owner's memory while the tensor core works on
+//     the next tile.  No NCCL call, no pack/unpack pass.
+//
+// Work is memory bound by construction (AI ~ N flop/byte); the tensor core only has to
+// stay off the critical path, which is why one CTA per SM with M=128 UMMA is sufficient.
+#include "sm100_ptx.cuh"
+#include "dft_gemm.h"
+
+namespace dfno {
+
+static constexpr int kTileM = 128;
+static constexpr int kBlockK = 64;                 // bf16 elements per 128-byte swizzle row
+static constexpr int kNumThreads = 192;            // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+static constexpr uint32_t kTmemCols = 512;
+static constexpr int kMaxStages = 4;
+
+struct SmemLayout {
+  uint32_t b_bytes;       // kblocks * n_pad * 128
+  uint32_t a_tile_bytes;  // kblocks * 16384
+  uint32_t stages;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmParams p, const SmemLayout L) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + L.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + L.stages * L.a_tile_bytes);
+  uint64_t* full = bars;                      // [stages]   TMA -> MMA
+  uint64_t* empty = bars + kMaxStages;        // [stages]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * kMaxStages;    // [2]        MMA -> epilogue
+  uint64_t* tempty = tfull + 2;               // [2]        epilogue -> MMA
+  uint64_t* bfull = tempty + 2;               // [1]        B resident
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kblocks = p.k_pad / kBlockK;
+  const int num_tiles = (p.M + kTileM - 1) / kTileM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (uint32_t s = 0; s < L.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4);                 // one arrival per epilogue warp
+    mbar_init(&tempty[1], 4);
+    mbar_init(bfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_holder);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bfull, L.b_bytes);
+      for (int kb = 0; kb < kblocks; ++kb)
+        tma_load_2d(smem_b + kb * p.n_pad * 128, &tmB, bfull, kb * kBlockK, 0);
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], L.a_tile_bytes);
+        uint8_t* dst = smem_a + s * L.a_tile_bytes;
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d(dst + kb * (kTileM * 128), &tmA, &full[s], kb * kBlockK, tile * kTileM);
+        if (++s == L.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad);
+    const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
+    mbar_wait(bfull, 0);
+    uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_ph ^ 1);
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_base = smem_u32(smem_a + s * L.a_tile_bytes);
+        const uint32_t b_base = smem_u32(smem_b);
+        const uint32_t d_tmem = tmem_base + acc * p.n_pad;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int kb = ks >> 2, kk = ks & 3;
+          const uint64_t adesc = umma_smem_desc_k128(a_base + kb * (kTileM * 128) + kk * 32);
+          const uint64_t bdesc = umma_smem_desc_k128(b_base + kb * (p.n_pad * 128) + kk * 32);
+          umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);               // smem stage may be refilled once the MMAs retire
+        umma_commit(&tfull[acc]);             // accumulator ready for the epilogue
+      }
+      __syncwarp();
+      if (++s == L.stages) { s = 0; ph ^= 1; }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global / peer memory ==========
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int r_in_tile = q * 32 + lane;
+    uint32_t acc = 0, acc_ph = 0;
+    const int npairs = p.N >> 1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long row = static_cast<long long>(tile) * kTileM + r_in_tile;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull[acc], acc_ph);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_pad;
+
+      if (p.epi.mode == EPI_ROWMAJOR) {
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          const int ncol = p.epi.vec_ok ? min(16, p.N - c0) : -min(16, p.N - c0);
+          if (p.epi.add_src != nullptr) {
+            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) +
+                                     row * p.epi.ld_add + c0;
+            if (ncol == 16) {
+              const uint4 u0 = *reinterpret_cast<const uint4*>(a);
+              const uint4 u1 = *reinterpret_cast<const uint4*>(a + 8);
+              const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 t = unpack_bf16x2(w[i]);
+                f[2 * i] += t.x;
+                f[2 * i + 1] += t.y;
+              }
+            } else {
+              for (int i = 0; i < abs(ncol); ++i) f[i] += __bfloat162float(a[i]);
+            }
+          }
+          if (p.epi.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.epi.peers[0]) + row * p.epi.ldc + c0;
+            if (ncol == 16) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              for (int i = 0; i < abs(ncol); ++i) o[i] = f[i];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + row * p.epi.ldc + c0;
+            if (ncol == 16) {
+              uint4 u0, u1;
+              u0.x = pack_bf16x2(f[0], f[1]);   u0.y = pack_bf16x2(f[2], f[3]);
+              u0.z = pack_bf16x2(f[4], f[5]);   u0.w = pack_bf16x2(f[6], f[7]);
+              u1.x = pack_bf16x2(f[8], f[9]);   u1.y = pack_bf16x2(f[10], f[11]);
+              u1.z = pack_bf16x2(f[12], f[13]); u1.w = pack_bf16x2(f[14], f[15]);
+              reinterpret_cast<uint4*>(o)[0] = u0;
+              reinterpret_cast<uint4*>(o)[1] = u1;
+            } else {
+              for (int i = 0; i < abs(ncol); ++i) o[i] = __float2bfloat16(f[i]);
+            }
+          }
+        }
+      } else {
+        // ---- pair scatter: (re, im) pairs to a mixed-radix address, possibly on a peer GPU
+        long long roff = p.epi.base_off;
+        int rpeer = 0;
+        {
+          long long r = row;
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            if (l < p.epi.nrl) {
+              const int radix = p.epi.R[l];
+              int d = (l == p.epi.nrl - 1) ? static_cast<int>(r) : static_cast<int>(r % radix);
+              r /= radix;
+              if (p.epi.peer_sel == PEER_BY_ROW && l == p.epi.peer_lvl) {
+                rpeer = d / p.epi.peer_div;
+                d -= rpeer * p.epi.peer_div;
+              }
+              roff += static_cast<long long>(d) * p.epi.SR[l];
+            }
+          }
+        }
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int j = (c0 >> 1) + i;
+            if (j < npairs) {
+              int peer = rpeer;
+              if (p.epi.peer_sel == PEER_BY_COL) {
+                peer = j / p.epi.peer_div;
+                j -= peer * p.epi.peer_div;
+              }
+              const int j0 = j % p.epi.J[0];
+              const int j1 = j / p.epi.J[0];
+              const long long off = roff + j0 * p.epi.SJ[0] + j1 * p.epi.SJ[1];
+              uint32_t* o = reinterpret_cast<uint32_t*>(
+                  reinterpret_cast<__nv_bfloat16*>(p.epi.peers[peer]) + off);
+              *o = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+    if (p.epi.peer_sel != PEER_NONE) __threadfence_system();   // publish peer stores
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dim = K elements (contiguous), outer = rows with pitch ld elements.
+static int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t ld_elems,
+                       uint32_t box_inner, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, GemmParams p, int num_sms,
+                            cudaStream_t stream) {
+  if (p.M <= 0) return nullptr;
+  if (p.n_pad % 16 || p.n_pad < 16 || p.n_pad > 256) return "n_pad must be a multiple of 16 in [16,256]";
+  if (p.k_pad % kBlockK || p.k_pad < kBlockK || p.k_pad > 512) return "k_pad must be a multiple of 64 in [64,512]";
+  if (p.K > p.k_pad || p.N > p.n_pad) return "K/N exceed padded operator";
+  if ((lda * 2) % 16) return "A row pitch must be a multiple of 16 bytes";
+  if (reinterpret_cast<uintptr_t>(A) % 16 || reinterpret_cast<uintptr_t>(Bmat) % 16) return "A/B base must be 16B aligned";
+  if (p.M > (1ll << 31) - 256) return "M too large for one launch";
+
+  if (p.epi.mode == EPI_ROWMAJOR) {
+    const long long esz = p.epi.out_fp32 ? 4 : 2;
+    bool ok = (p.epi.ldc * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(p.epi.peers[0]) % 16 == 0;
+    if (p.epi.add_src)
+      ok = ok && (p.epi.ld_add * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(p.epi.add_src) % 16 == 0;
+    p.epi.vec_ok = ok ? 1 : 0;
+  }
+  SmemLayout L;
+  const int kblocks = p.k_pad / kBlockK;
+  L.b_bytes = static_cast<uint32_t>(kblocks) * p.n_pad * 128;
+  L.a_tile_bytes = static_cast<uint32_t>(kblocks) * kTileM * 128;
+  const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  if (L.b_bytes + 2 * L.a_tile_bytes > budget) return "operator too large for shared memory";
+  L.stages = (budget - L.b_bytes) / L.a_tile_bytes;
+  if (L.stages > kMaxStages) L.stages = kMaxStages;
+  uint32_t smem_bytes = L.b_bytes + L.stages * L.a_tile_bytes + 256;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;     // force one CTA per SM (TMEM: 512 cols)
+
+  CUtensorMap tmA, tmB;
+  // A: the K tail beyond p.K (up to k_pad) and the M tail are zero-filled by TMA
+  if (make_map_2d(&tmA, A, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M), static_cast<uint64_t>(lda),
+                  kBlockK, kTileM))
+    return "cuTensorMapEncodeTiled(A) failed";
+  if (make_map_2d(&tmB, Bmat, static_cast<uint64_t>(p.k_pad), static_cast<uint64_t>(p.n_pad),
+                  static_cast<uint64_t>(p.k_pad), kBlockK, static_cast<uint32_t>(p.n_pad)))
+    return "cuTensorMapEncodeTiled(B) failed";
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(dft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return "cudaFuncSetAttribute(max dynamic smem) failed";
+    attr_set = true;
+  }
+  const int num_tiles = static_cast<int>((p.M + kTileM - 1) / kTileM);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  dft_gemm_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, p, L);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace dfno
