@@ -62,7 +62,8 @@ void dft_gemm(const at::Tensor& A, int64_t M, int64_t K, int64_t lda, const at::
 
 }  // namespace
 
-void register_pointwise(pybind11::module& m);   // pointwise_bindings.cpp
+void register_ops(pybind11::module& m);    // ops_bindings.cpp
+void register_symm(pybind11::module& m);   // symm_mem.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "dfno_b200 sm_100a kernels";
@@ -70,5 +71,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("A"), py::arg("M"), py::arg("K"), py::arg("lda"), py::arg("Bmat"), py::arg("N"),
         py::arg("epi"), py::arg("peer_ptrs"), py::arg("add_src") = c10::nullopt, py::arg("ld_add") = 0,
         py::arg("max_ctas") = 0);
-  register_pointwise(m);
+  register_ops(m);
+  register_symm(m);
 }

@@ -1,7 +1,49 @@
 // Launchers of the torch-free CUDA translation units (pointwise / spectral / optimizer / p2p).
+// Every launcher returns nullptr on success or a static error string.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace dfno {
+
+struct LiftDims {
+  int B, Cin, Tin;     // input  [B, Cin, X, Y, Z, Tin]   (reference layout, t contiguous)
+  int C, T;            // output [B*C, X, Y, T, Z]        (engine layout, z contiguous)
+  int X, Y, Z;         // local spatial extents
+};
+
+const char* lift_fwd(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
+                     const float* b2, void* h, LiftDims d, int num_sms, cudaStream_t s);
+const char* lift_bwd(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
+                     const float* b2, const void* dh, float* gW1, float* gb1, float* gW2, float* gb2,
+                     LiftDims d, int num_sms, cudaStream_t s);
+// S = X*Y*T*Z elements per (b, c) slab.  out / out_cl may be null.
+const char* bypass_gelu_fwd(const void* h, void* spec_pre, const float* W, void* out, void* out_cl, int cl_pitch,
+                            int B, int C, long long S, int save_pre, int num_sms, cudaStream_t s);
+const char* bypass_gelu_bwd(const void* dout, const void* dout_cl, int cl_pitch, const void* pre, const float* W,
+                            void* dpre, void* dhb, int B, int C, long long S, int num_sms, cudaStream_t s);
+
+// spectral channel mixing over the local mode slab: x,y bf16 [B, C, Q, 2]; w fp32 [C, C, Q, 2]
+const char* spectral_mix_fwd(const void* x, const float* w, void* y, int B, int C, long long Q, cudaStream_t s);
+// dx = dy * conj(w) ; dw (+)= conj(x) * dy summed over the batch
+const char* spectral_mix_bwd(const void* x, const float* w, const void* dy, void* dx, float* dw, int accumulate,
+                             int B, int C, long long Q, cudaStream_t s);
+
+// fused Adam over one flat fp32 parameter buffer (decoupled=0: L2 weight decay like torch.optim.Adam)
+const char* adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, float bias1, float bias2, float grad_scale, int num_sms,
+                      cudaStream_t s);
+
+// cross-GPU flag barrier over NVLink-mapped signal pads: every rank bumps its slot on each
+// peer to `epoch`, then waits until all of its own slots reached `epoch`.
+const char* p2p_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, int rank, int world, uint32_t epoch,
+                        cudaStream_t s);
+// sum-all-reduce of a small fp32 vector through peer reads (every rank reads all peers' copies)
+const char* p2p_allreduce_small(float* const* peer_bufs, float* out, long long n, int rank, int world,
+                                cudaStream_t s);
+
+// K-reduction GEMM: D[i, j] (+)= sum_k A[i, k] * B[j, k]; A: [Ma<=128, K], B: [Nb<=256, K] bf16 K-major.
+const char* kreduce_gemm(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, long long K,
+                         float* D, long long ldd, int num_sms, cudaStream_t s);
+
 }  // namespace dfno

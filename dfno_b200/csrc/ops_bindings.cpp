@@ -1,0 +1,135 @@
+// Bindings for the pointwise / spectral / optimizer / p2p launchers (kernels.h).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include "kernels.h"
+
+namespace {
+
+int sm_count() {
+  static int n = 0;
+  if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
+}
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+void check(const char* err, const char* what) { TORCH_CHECK(err == nullptr, what, ": ", err ? err : ""); }
+const float* fptr(const at::Tensor& t) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous(), "expected contiguous CUDA fp32 tensor");
+  return t.data_ptr<float>();
+}
+float* fptr_mut(at::Tensor& t) { return const_cast<float*>(fptr(t)); }
+void* bptr(const at::Tensor& t) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16, "expected CUDA bf16 tensor");
+  return t.data_ptr();
+}
+
+dfno::LiftDims lift_dims(const std::vector<int64_t>& d) {
+  TORCH_CHECK(d.size() == 8, "dims = [B, Cin, Tin, C, T, X, Y, Z]");
+  dfno::LiftDims L;
+  L.B = d[0]; L.Cin = d[1]; L.Tin = d[2]; L.C = d[3]; L.T = d[4]; L.X = d[5]; L.Y = d[6]; L.Z = d[7];
+  return L;
+}
+
+void lift_fwd(const at::Tensor& x, const at::Tensor& W1, const at::Tensor& b1, const at::Tensor& W2,
+              const at::Tensor& b2, at::Tensor& h, const std::vector<int64_t>& dims) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous(), "x must be a contiguous CUDA tensor");
+  TORCH_CHECK(x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16, "x must be fp32 or bf16");
+  c10::cuda::CUDAGuard guard(x.device());
+  check(dfno::lift_fwd(x.data_ptr(), x.scalar_type() == at::kBFloat16, fptr(W1), fptr(b1), fptr(W2), fptr(b2),
+                       bptr(h), lift_dims(dims), sm_count(), cur_stream()), "lift_fwd");
+}
+
+void lift_bwd(const at::Tensor& x, const at::Tensor& W1, const at::Tensor& b1, const at::Tensor& W2,
+              const at::Tensor& b2, const at::Tensor& dh, at::Tensor& gW1, at::Tensor& gb1, at::Tensor& gW2,
+              at::Tensor& gb2, const std::vector<int64_t>& dims) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous(), "x must be a contiguous CUDA tensor");
+  c10::cuda::CUDAGuard guard(x.device());
+  check(dfno::lift_bwd(x.data_ptr(), x.scalar_type() == at::kBFloat16, fptr(W1), fptr(b1), fptr(W2), fptr(b2),
+                       bptr(dh), fptr_mut(gW1), fptr_mut(gb1), fptr_mut(gW2), fptr_mut(gb2), lift_dims(dims),
+                       sm_count(), cur_stream()), "lift_bwd");
+}
+
+void bypass_gelu_fwd(const at::Tensor& h, at::Tensor& spec_pre, const at::Tensor& W,
+                     const c10::optional<at::Tensor>& out, const c10::optional<at::Tensor>& out_cl, int64_t cl_pitch,
+                     int64_t B, int64_t C, int64_t S, bool save_pre) {
+  c10::cuda::CUDAGuard guard(h.device());
+  check(dfno::bypass_gelu_fwd(bptr(h), bptr(spec_pre), fptr(W), out ? bptr(*out) : nullptr,
+                              out_cl ? bptr(*out_cl) : nullptr, static_cast<int>(cl_pitch), static_cast<int>(B),
+                              static_cast<int>(C), S, save_pre ? 1 : 0, sm_count(), cur_stream()), "bypass_gelu_fwd");
+}
+
+void bypass_gelu_bwd(const c10::optional<at::Tensor>& dout, const c10::optional<at::Tensor>& dout_cl, int64_t cl_pitch,
+                     const at::Tensor& pre, const at::Tensor& W, at::Tensor& dpre, at::Tensor& dhb, int64_t B,
+                     int64_t C, int64_t S) {
+  TORCH_CHECK(dout.has_value() != dout_cl.has_value(), "give exactly one of dout / dout_cl");
+  c10::cuda::CUDAGuard guard(pre.device());
+  check(dfno::bypass_gelu_bwd(dout ? bptr(*dout) : nullptr, dout_cl ? bptr(*dout_cl) : nullptr,
+                              static_cast<int>(cl_pitch), bptr(pre), fptr(W), bptr(dpre), bptr(dhb),
+                              static_cast<int>(B), static_cast<int>(C), S, sm_count(), cur_stream()), "bypass_gelu_bwd");
+}
+
+void spectral_mix_fwd(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, int64_t B, int64_t C, int64_t Q) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check(dfno::spectral_mix_fwd(bptr(x), fptr(w), bptr(y), static_cast<int>(B), static_cast<int>(C), Q, cur_stream()),
+        "spectral_mix_fwd");
+}
+
+void spectral_mix_bwd(const at::Tensor& x, const at::Tensor& w, const at::Tensor& dy, at::Tensor& dx, at::Tensor& dw,
+                      bool accumulate, int64_t B, int64_t C, int64_t Q) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check(dfno::spectral_mix_bwd(bptr(x), fptr(w), bptr(dy), bptr(dx), fptr_mut(dw), accumulate ? 1 : 0,
+                               static_cast<int>(B), static_cast<int>(C), Q, cur_stream()), "spectral_mix_bwd");
+}
+
+void adam_step(at::Tensor& p, const at::Tensor& g, at::Tensor& m, at::Tensor& v, double lr, double beta1, double beta2,
+               double eps, double weight_decay, int64_t step, double grad_scale) {
+  TORCH_CHECK(p.numel() == g.numel() && p.numel() == m.numel() && p.numel() == v.numel(), "adam: size mismatch");
+  c10::cuda::CUDAGuard guard(p.device());
+  const double bias1 = 1.0 - std::pow(beta1, static_cast<double>(step));
+  const double bias2 = 1.0 - std::pow(beta2, static_cast<double>(step));
+  check(dfno::adam_step(fptr_mut(p), fptr(g), fptr_mut(m), fptr_mut(v), p.numel(), static_cast<float>(lr),
+                        static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(eps),
+                        static_cast<float>(weight_decay), static_cast<float>(bias1), static_cast<float>(bias2),
+                        static_cast<float>(grad_scale), sm_count(), cur_stream()), "adam_step");
+}
+
+void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t epoch) {
+  const int world = static_cast<int>(flag_ptrs.size());
+  uint32_t* peers[8];
+  for (int i = 0; i < 8; ++i) peers[i] = reinterpret_cast<uint32_t*>(flag_ptrs[i < world ? i : 0]);
+  check(dfno::p2p_barrier(peers, peers[rank], static_cast<int>(rank), world, static_cast<uint32_t>(epoch),
+                          cur_stream()), "p2p_barrier");
+}
+
+void p2p_allreduce_small(const std::vector<int64_t>& buf_ptrs, at::Tensor& out, int64_t n, int64_t rank) {
+  const int world = static_cast<int>(buf_ptrs.size());
+  float* peers[8];
+  for (int i = 0; i < 8; ++i) peers[i] = reinterpret_cast<float*>(buf_ptrs[i < world ? i : 0]);
+  check(dfno::p2p_allreduce_small(peers, fptr_mut(out), n, static_cast<int>(rank), world, cur_stream()),
+        "p2p_allreduce_small");
+}
+
+// D[Ma, Nb] (fp32, pre-zeroed or accumulated) += A[Ma, K] * B[Nb, K]^T, K contiguous
+void kreduce_gemm(const at::Tensor& A, int64_t lda, int64_t Ma, const at::Tensor& Bm, int64_t ldb, int64_t Nb,
+                  int64_t K, at::Tensor& D) {
+  TORCH_CHECK(D.dim() == 2 && D.size(0) >= Ma && D.size(1) >= Nb, "D too small");
+  c10::cuda::CUDAGuard guard(A.device());
+  check(dfno::kreduce_gemm(bptr(A), lda, static_cast<int>(Ma), bptr(Bm), ldb, static_cast<int>(Nb), K, fptr_mut(D),
+                           D.stride(0), sm_count(), cur_stream()), "kreduce_gemm");
+}
+
+}  // namespace
+
+void register_ops(pybind11::module& m) {
+  m.def("lift_fwd", &lift_fwd);
+  m.def("lift_bwd", &lift_bwd);
+  m.def("bypass_gelu_fwd", &bypass_gelu_fwd);
+  m.def("bypass_gelu_bwd", &bypass_gelu_bwd);
+  m.def("spectral_mix_fwd", &spectral_mix_fwd);
+  m.def("spectral_mix_bwd", &spectral_mix_bwd);
+  m.def("adam_step", &adam_step);
+  m.def("p2p_barrier", &p2p_barrier);
+  m.def("p2p_allreduce_small", &p2p_allreduce_small);
+  m.def("kreduce_gemm", &kreduce_gemm);
+}

@@ -1,0 +1,71 @@
+// p2p.cu -- peer-memory (NVLink 5 / NVSwitch) synchronisation and small collectives.
+//
+// Symmetric buffers (symm_mem.cpp) give every rank a device pointer to every peer's buffer.
+// The fused GEMM epilogues store tiles straight into those; what remains is ordering:
+//
+//   p2p_barrier        : flag exchange.  Rank r writes `epoch` into slot r of every peer's
+//                        flag array (st.release.sys after a system fence, so all peer stores
+//                        issued earlier on the stream are visible), then spins until all of
+//                        its own slots reached `epoch` (ld.acquire.sys).  ~2 NVLink latencies,
+//                        no host involvement, capturable in a CUDA graph.
+//   p2p_allreduce_small: sum of a small fp32 vector across ranks by reading every peer's
+//                        copy in rank order (bitwise identical result on all ranks).  This is
+//                        the gradient reduction of the replicated pointwise weights -- the
+//                        Broadcast/SumReduce pair of the reference's BroadcastedLinear
+//                         collapses to one such call per optimizer step.
+#include "sm100_ptx.cuh"
+#include "kernels.h"
+
+namespace dfno {
+namespace {
+
+struct PeerFlags { uint32_t* p[8]; };
+struct PeerBufs { const float* p[8]; };
+
+__global__ void p2p_barrier_kernel(PeerFlags peers, uint32_t* my_flags, int rank, int world, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();
+    st_release_sys(peers.p[r] + rank, epoch);
+    // epochs only grow; signed difference tolerates wrap-around
+    while (static_cast<int32_t>(ld_acquire_sys(my_flags + r) - epoch) < 0) {
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(PeerBufs bufs, float* __restrict__ out, long long n, int world) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < world; ++r) acc += bufs.p[r][i];
+    out[i] = acc;
+  }
+}
+
+}  // namespace
+
+const char* p2p_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, int rank, int world, uint32_t epoch,
+                        cudaStream_t s) {
+  if (world < 1 || world > 8) return "p2p_barrier: world size must be 1..8";
+  PeerFlags pf;
+  for (int i = 0; i < 8; ++i) pf.p[i] = peer_flags[i < world ? i : 0];
+  p2p_barrier_kernel<<<1, 32, 0, s>>>(pf, my_flags, rank, world, epoch);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+const char* p2p_allreduce_small(float* const* peer_bufs, float* out, long long n, int rank, int world,
+                                cudaStream_t s) {
+  if (world < 1 || world > 8) return "p2p_allreduce: world size must be 1..8";
+  PeerBufs pb;
+  for (int i = 0; i < 8; ++i) pb.p[i] = peer_bufs[i < world ? i : 0];
+  long long blocks = (n + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  if (blocks < 1) blocks = 1;
+  p2p_allreduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(pb, out, n, world);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace dfno

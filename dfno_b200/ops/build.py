@@ -21,7 +21,7 @@ NAME = "dfno_b200_C"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--expt-relaxed-constexpr", "-Xptxas", "-v",
+    "--expt-relaxed-constexpr", "--extended-lambda", "-Xptxas", "-v",
 ]
 
 _lock = threading.Lock()
