@@ -1,5 +1,626 @@
-"""Placeholder hook, replaced once the sm_100a engine lands."""
+"""Fused sm_100a engine for the model-parallel FNO (``backend="fused"``).
+
+Same function as :class:`dfno_b200.models.fno.DistributedFNO` (spec: SURVEY.md §3.1), but
+organised around B200 hardware instead of around ``torch.fft`` + MPI:
+
+* **Layout.**  Activations live as ``h[b*C + c, x, y_local, t, z]`` in bf16 with ``z``
+  contiguous.  The public tensors keep the reference layout ``[B, C, X, Y, Z, T]``; the lift
+  and the projection head are the only places the layouts meet, so no transpose pass exists.
+* **Transforms are GEMMs.**  Each truncated (inverse) DFT stage is ``lines x K`` times a tiny
+  resident operator on tcgen05 (``csrc/dft_gemm_sm100.cu``), written by its epilogue directly
+  in the layout -- and onto the GPU -- the next stage wants.  Complex data is interleaved
+  (re, im) so a complex DFT is one real GEMM (``ops/operators.py``).
+* **Pencil transposes are fused.**  With the field split along ``y`` over ``P`` GPUs, stage m
+  (axes z, t) is local; its last GEMM scatters every (kz, kt) mode slab straight into the
+  owning GPU's symmetric buffer over NVLink (Repartition R2), stage y (axes y, x), the
+  per-mode channel mixing and the inverse stage y run on the mode-sharded data, and the
+  inverse y-GEMM scatters back (R3).  R1/R4 are identities for a y-pencil.  Ordering is a
+  device-side flag barrier (``csrc/p2p.cu``); there is no NCCL call on the hot path.
+* **Weights.**  All parameters sit in ONE flat fp32 buffer ``theta``: the pointwise weights
+  (replicated on every rank, kept identical by all-reducing their tiny gradient once per
+  step -- the reference broadcasts each of them every forward) followed by this rank's
+  spectral shard (modes ``kz in [rank*kzl, (rank+1)*kzl)``, all ``kt, ky, kx``).  One fused
+  Adam launch updates the model.
+* **Backward is the same chain.**  The adjoint of every stage has the shape of its mirror
+  stage, so the backward runs the identical kernel sequence with transposed operators.
+
+Reference call stack being replaced: ``/root/reference/dfno/dfno.py:241-291`` (block),
+``:330-353`` (model).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import operators as OPS
+from ..ops.gemm import ScatterSpec, pad_operator
+from ..parallel.partition import Partition, create_root_partition
+
+__all__ = ["FusedDistributedFNO", "FusedAdam", "supports", "wants", "EnginePlan"]
+
+SUPPORTED_WIDTHS = (4, 8, 12, 16, 20, 24, 32)
+HEAD_HIDDEN = 128
 
 
-def wants(args, kwargs, backend) -> bool:
-    return False
+# =====================================================================================
+# eligibility
+# =====================================================================================
+
+def _pencil_axis(grid: Sequence[int]) -> Optional[int]:
+    """Return the partitioned axis if ``grid`` is a supported 1 x P pencil, else None."""
+    g = [int(v) for v in grid]
+    if len(g) != 6:
+        return None
+    parted = [i for i, v in enumerate(g) if v > 1]
+    if not parted:
+        return 3
+    if parted == [3]:
+        return 3
+    return None
+
+
+def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
+             modes: Sequence[int]) -> Tuple[bool, str]:
+    """Can the fused engine run this configuration?  Returns ``(ok, reason)``."""
+    if P_x.dim != 6:
+        return False, "fused engine covers 3-D + time fields (6-D tensors)"
+    if _pencil_axis(P_x.shape) is None:
+        return False, "fused engine needs a (1,1,1,P,1,1) y-pencil partition"
+    P = int(P_x.shape[3])
+    B, Cin, X, Y, Z, Tin = [int(s) for s in in_shape]
+    T = int(out_timesteps)
+    mx, my, mz, mt = [int(m) for m in modes]
+    if width not in SUPPORTED_WIDTHS:
+        return False, f"width {width} not in {SUPPORTED_WIDTHS}"
+    if P > 8:
+        return False, "at most 8 peers (one NVSwitch box)"
+    if Y % P or (2 * mz) % P:
+        return False, "Y and 2*modes_z must divide evenly over the pencil"
+    if Cin > 4 or Cin * Tin > 32:
+        return False, "lift kernel covers Cin <= 4 and Cin*Tin <= 32"
+    if Z % 8 or T % 4 or Y % 4 or X % 4 or mx % 2 or my % 2 or mz % 2:
+        return False, "extents must satisfy Z%8 = T%4 = X%4 = Y%4 = 0 and even modes (TMA pitch alignment)"
+    if 2 * mx > X or 2 * my > Y or 2 * mz > Z or mt > T // 2 + 1:
+        return False, "mode counts exceed the axes"
+    if max(2 * X, 2 * Y, Z, 2 * T) > 512 or max(2 * X, 2 * Y, Z) > 256 and False:
+        return False, "axis too long for a single resident operator"
+    if max(Z, 2 * T, 2 * X, 2 * Y) > 256:
+        return False, "transformed axes up to 128 complex / 256 real samples are supported"
+    return True, ""
+
+
+def wants(args, kwargs, backend: str) -> bool:
+    """Should ``DistributedFNO(...)`` be served by the fused engine?"""
+    if backend not in ("auto", "fused"):
+        return False
+    names = ["P_x", "in_shape", "out_timesteps", "width", "modes", "num_blocks", "device", "dtype"]
+    cfg = dict(zip(names, args))
+    cfg.update(kwargs)
+    if "P_x" not in cfg or "in_shape" not in cfg:
+        return False
+    device = torch.device(cfg.get("device", "cpu"))
+    dtype = cfg.get("dtype", torch.float32)
+    ok, why = supports(cfg["P_x"], cfg["in_shape"], cfg["out_timesteps"], cfg["width"], cfg["modes"])
+    if backend == "fused":
+        if not ok:
+            raise ValueError(f"backend='fused' requested but unsupported: {why}")
+        if device.type != "cuda":
+            raise ValueError("backend='fused' needs a CUDA device")
+        return True
+    return ok and device.type == "cuda" and dtype == torch.bfloat16 and cfg.get("plan", None) in (None, "balanced")
+
+
+# =====================================================================================
+# static plan: shapes, buffers, stage descriptors
+# =====================================================================================
+
+class EnginePlan:
+    """All integer bookkeeping of one rank; no tensors, no CUDA -- unit-testable on CPU."""
+
+    def __init__(self, B, Cin, Tin, C, T, X, Y, Z, modes, world=1, rank=0, hidden=HEAD_HIDDEN):
+        self.B, self.Cin, self.Tin, self.C, self.T = B, Cin, Tin, C, T
+        self.X, self.Y, self.Z = X, Y, Z
+        self.mx, self.my, self.mz, self.mt = [int(m) for m in modes]
+        self.world, self.rank, self.H = world, rank, hidden
+        self.Yl = Y // world
+        self.y_off = rank * self.Yl
+        self.KX, self.KY, self.KZ = 2 * self.mx, 2 * self.my, 2 * self.mz
+        self.kzl = self.KZ // world
+        self.kz_off = rank * self.kzl
+        self.mtp = (self.mt + 3) // 4 * 4
+        self.BC = B * C
+        self.S = X * self.Yl * T * Z                       # positions per (b, c) slab
+        self.npos = B * self.S
+        self.Q = self.kzl * self.mt * self.KY * self.KX    # local modes
+        self.CP = (C + 7) // 8 * 8                         # channels-last pitch (16-byte rows)
+        # element counts (bf16 unless noted)
+        BC, Yl, kzl, mt, mtp = self.BC, self.Yl, self.kzl, self.mt, self.mtp
+        self.n_act = BC * self.S
+        self.n_Z1 = BC * X * self.KZ * Yl * T * 2
+        self.n_S1 = BC * kzl * mt * X * Y * 2
+        self.n_S2 = BC * kzl * mt * self.KY * X * 2
+        self.n_S3 = BC * self.Q * 2
+        self.n_T2 = BC * X * kzl * mt * self.KY * 2
+        self.n_T1 = BC * X * Yl * self.KZ * mtp * 2
+        self.n_U = BC * X * Yl * T * self.KZ * 2
+        # flat parameter layout (fp32 elements)
+        self.segments: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+
+        def seg(name, *shape):
+            nonlocal off
+            self.segments[name] = (off, tuple(shape))
+            off += int(np.prod(shape))
+
+        seg("linear1.W", T, Tin); seg("linear1.b", T)
+        seg("linear2.W", C, Cin); seg("linear2.b", C)
+        self.num_blocks = None
+
+    def finish(self, num_blocks: int) -> None:
+        off = sum(int(np.prod(s)) for _, s in self.segments.values())
+        C, H = self.C, self.H
+
+        def seg(name, *shape):
+            nonlocal off
+            self.segments[name] = (off, tuple(shape))
+            off += int(np.prod(shape))
+
+        for k in range(num_blocks):
+            seg(f"blocks.{k}.linear.W", C, C)
+        seg("linear3.W", H, C); seg("linear3.b", H)
+        seg("linear4.W", 1, H); seg("linear4.b", 1)
+        self.n_small = (off + 63) // 64 * 64               # replicated segment (all-reduced)
+        off = self.n_small
+        for k in range(num_blocks):
+            seg(f"blocks.{k}.spectral", C, C, self.Q, 2)
+        self.n_theta = off
+        self.num_blocks = num_blocks
+
+    # ---------------------------------------------------------------- stage descriptors
+    def chain(self) -> List[dict]:
+        """The nine GEMM stages of one spectral convolution (forward *or* adjoint: only the
+        operator matrices and the end buffers differ).  Strides in bf16 elements."""
+        BC, X, Y, Z, T = self.BC, self.X, self.Y, self.Z, self.T
+        Yl, KX, KY, KZ, kzl, mt, mtp = self.Yl, self.KX, self.KY, self.KZ, self.kzl, self.mt, self.mtp
+        m_loc = kzl * mt
+        st = []
+        st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
+                       scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * T), (BC * X, KZ * Yl * T * 2)],
+                                           cols=(KZ, Yl * T * 2, 0))))
+        st.append(dict(name="G1b", src="Z1", dst="S1", M=BC * X * KZ * Yl, K=2 * T, lda=2 * T, N=2 * mt, op="G1b",
+                       scatter=ScatterSpec(rows=[(Yl, 2), (KZ, mt * X * Y * 2), (X, Y * 2), (BC, m_loc * X * Y * 2)],
+                                           cols=(mt, X * Y * 2, 0), peer=("row", 1, kzl), base_off=self.y_off * 2),
+                       peer_dst=True, barrier_after=True))
+        st.append(dict(name="G2", src="S1", dst="S2", M=BC * m_loc * X, K=2 * Y, lda=2 * Y, N=2 * KY, op="G2",
+                       scatter=ScatterSpec(rows=[(X, 2), (BC * m_loc, KY * X * 2)], cols=(KY, X * 2, 0))))
+        st.append(dict(name="G3", src="S2", dst="S3", M=BC * m_loc * KY, K=2 * X, lda=2 * X, N=2 * KX, op="G3",
+                       ldc=2 * KX))
+        st.append(dict(name="mix"))
+        st.append(dict(name="iG3", src="S4", dst="T2", M=BC * m_loc * KY, K=2 * KX, lda=2 * KX, N=2 * X, op="iG3",
+                       scatter=ScatterSpec(rows=[(KY, 2), (m_loc, KY * 2), (BC, X * m_loc * KY * 2)],
+                                           cols=(X, m_loc * KY * 2, 0))))
+        st.append(dict(name="iG2", src="T2", dst="T1", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
+                       scatter=ScatterSpec(rows=[(mt, 2), (kzl, mtp * 2), (X, Yl * KZ * mtp * 2),
+                                                 (BC, X * Yl * KZ * mtp * 2)],
+                                           cols=(Yl, KZ * mtp * 2, 0), peer=("col", Yl),
+                                           base_off=self.kz_off * mtp * 2),
+                       peer_dst=True, barrier_after=True))
+        st.append(dict(name="iG1b", src="T1", dst="U", M=BC * X * Yl * KZ, K=2 * mt, lda=2 * mtp, N=2 * T, op="iG1b",
+                       scatter=ScatterSpec(rows=[(KZ, 2), (BC * X * Yl, T * KZ * 2)], cols=(T, KZ * 2, 0))))
+        st.append(dict(name="iG1a", src="U", dst="dst", M=BC * X * Yl * T, K=2 * KZ, lda=2 * KZ, N=Z, op="iG1a",
+                       ldc=Z))
+        return st
+
+    def operators(self) -> Dict[str, torch.Tensor]:
+        """Forward-chain operators (float64) and their adjoint-chain counterparts (``*_adj``)."""
+        X, Y, Z, T = self.X, self.Y, self.Z, self.T
+        f = {
+            "G1a": OPS.fwd_real_to_complex(Z, self.mz), "G1b": OPS.fwd_complex(T, self.mt, False),
+            "G2": OPS.fwd_complex(Y, self.my), "G3": OPS.fwd_complex(X, self.mx),
+            "iG3": OPS.inv_complex(X, self.mx), "iG2": OPS.inv_complex(Y, self.my),
+            "iG1b": OPS.inv_complex_hermitian(T, self.mt), "iG1a": OPS.inv_complex_to_real(Z, self.mz),
+        }
+        mirror = {"G1a": "iG1a", "G1b": "iG1b", "G2": "iG2", "G3": "iG3",
+                  "iG3": "G3", "iG2": "G2", "iG1b": "G1b", "iG1a": "G1a"}
+        out = dict(f)
+        for slot, src in mirror.items():       # the adjoint chain's stage in slot X is adj(mirror(X))
+            out[slot + "_adj"] = f[src].t().contiguous()
+        return out
+
+
+# =====================================================================================
+# the module
+# =====================================================================================
+
+class _FusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, theta, eng):
+        ctx.eng = eng
+        ctx.train = torch.is_grad_enabled() and theta.requires_grad
+        y = eng._forward(x, save=theta.requires_grad)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        # the engine writes straight into theta.grad's storage (no 2 GB autograd copy)
+        ctx.eng._backward(x, dy)
+        return None, None, None
+
+
+class FusedDistributedFNO(nn.Module):
+    """Drop-in ``DistributedFNO`` on the fused sm_100a engine.  Same constructor; the forward
+    takes this rank's ``[B, C_in, X, Y_local, Z, T_in]`` shard (fp32 or bf16, CUDA) and returns
+    ``[B, 1, X, Y_local, Z, T_out]`` in fp32."""
+
+    def __init__(self, P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
+                 modes: Sequence[int], num_blocks: int = 4, device=torch.device("cuda"),
+                 dtype=torch.bfloat16, plan: Optional[str] = None, backend: str = "fused",
+                 use_p2p: Optional[bool] = None):
+        super().__init__()
+        ok, why = supports(P_x, in_shape, out_timesteps, width, modes)
+        if not ok:
+            raise ValueError(f"fused engine cannot run this configuration: {why}")
+        from ..ops import build
+        self._C = build.load()                 # fails loudly if the extension is missing
+        self.P_x = P_x
+        self.in_shape = [int(s) for s in in_shape]
+        self.out_timesteps, self.width = int(out_timesteps), int(width)
+        self.modes = [int(m) for m in modes]
+        self.num_blocks = int(num_blocks)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("the fused engine needs a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = torch.bfloat16
+        self.block_in_shape = [self.in_shape[0], self.width, *self.in_shape[2:-1], self.out_timesteps]
+        B, Cin, X, Y, Z, Tin = self.in_shape
+        self.world = int(P_x.shape[3]) if P_x.active else 1
+        self.rank = int(P_x.index[3]) if P_x.active else 0
+        self.plan = EnginePlan(B, Cin, Tin, self.width, self.out_timesteps, X, Y, Z, self.modes,
+                               self.world, self.rank)
+        self.plan.finish(self.num_blocks)
+        pl = self.plan
+        self.dt_comm = 0.0
+
+        # ---- parameters: one flat fp32 buffer
+        theta = torch.zeros(pl.n_theta, device=self.device, dtype=torch.float32)
+        self.theta = nn.Parameter(theta)
+        self._init_parameters()
+
+        # ---- operators (bf16, padded) for the forward and the adjoint chain
+        self.ops = {k: pad_operator(v, device=self.device) for k, v in pl.operators().items()}
+
+        # ---- symmetric buffers + barrier
+        from ..runtime.symm import PeerBarrier, SymmetricBuffer
+        self.use_p2p = self.world > 1 if use_p2p is None else (use_p2p and self.world > 1)
+        grp = P_x.group
+        if self.world > 1:
+            self.sym_S1 = SymmetricBuffer(pl.n_S1 * 2, grp, self.rank, self.world, self.device.index)
+            self.sym_T1 = SymmetricBuffer(pl.n_T1 * 2, grp, self.rank, self.world, self.device.index)
+            self.sym_small = SymmetricBuffer(pl.n_small * 4, grp, self.rank, self.world, self.device.index)
+        else:
+            self.sym_S1 = self.sym_T1 = self.sym_small = None
+        self.barrier = PeerBarrier(grp, self.rank, self.world)
+
+        # ---- workspaces
+        bf = dict(device=self.device, dtype=torch.bfloat16)
+        self.ws = {
+            "Z1U": torch.empty(max(pl.n_Z1, pl.n_U), **bf),
+            "S1": self.sym_S1.view([pl.n_S1], torch.bfloat16) if self.world > 1 else torch.empty(pl.n_S1, **bf),
+            "T1": self.sym_T1.view([pl.n_T1], torch.bfloat16) if self.world > 1 else torch.empty(pl.n_T1, **bf),
+            "S2": torch.empty(pl.n_S2, **bf), "S3w": torch.empty(pl.n_S3, **bf),
+            "S4": torch.empty(pl.n_S3, **bf), "T2": torch.empty(pl.n_T2, **bf),
+        }
+        self._saved: Dict[str, torch.Tensor] = {}
+        self._train_bufs_ready = False
+        self.chain_desc = pl.chain()
+
+    # ------------------------------------------------------------------ parameters
+    def _seg(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, shape = self.plan.segments[name]
+        base = self.theta.data if base is None else base
+        return base[off:off + int(np.prod(shape))].view(shape)
+
+    def _init_parameters(self) -> None:
+        pl = self.plan
+        with torch.no_grad():
+            for name, (off, shape) in pl.segments.items():
+                t = self._seg(name)
+                if name.endswith(".spectral"):
+                    t.copy_(torch.rand(shape, device=self.device) / (self.width * self.width))
+                elif name.endswith(".W"):
+                    nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+                else:
+                    t.zero_()
+            if self.world > 1:            # replicated pointwise weights: everyone takes rank 0's draw
+                small = self.theta.data[:pl.n_small]
+                dist.broadcast(small, src=self.P_x.world_ranks[0], group=self.P_x.group)
+
+    def named_views(self) -> Dict[str, torch.Tensor]:
+        return {name: self._seg(name) for name in self.plan.segments}
+
+    # ------------------------------------------------------------------ buffers
+    def _ensure_train_buffers(self) -> None:
+        if self._train_bufs_ready:
+            return
+        pl = self.plan
+        bf = dict(device=self.device, dtype=torch.bfloat16)
+        nb = self.num_blocks
+        self._saved["h"] = [torch.empty(pl.n_act, **bf) for _ in range(nb)]       # block inputs
+        self._saved["pre"] = [torch.empty(pl.n_act, **bf) for _ in range(nb)]     # pre-activations
+        self._saved["S3"] = [torch.empty(pl.n_S3, **bf) for _ in range(nb)]       # spectra entering the mix
+        self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)                    # last block out, channels-last
+        self.ws["g"] = torch.empty(pl.n_act, **bf)
+        self.ws["dhb"] = torch.empty(pl.n_act, **bf)
+        self.ws["gcl"] = torch.empty(pl.npos, pl.CP, **bf)
+        self.grad_flat = torch.zeros(pl.n_theta, device=self.device, dtype=torch.float32)
+        self.accumulate_grads = False          # True: keep adding into theta.grad across backward calls
+        self._train_bufs_ready = True
+
+    def _ensure_eval_buffers(self) -> None:
+        if "eval_h" in self.ws:
+            return
+        pl = self.plan
+        bf = dict(device=self.device, dtype=torch.bfloat16)
+        self.ws["eval_h"] = [torch.empty(pl.n_act, **bf) for _ in range(2)]
+        self.ws["eval_pre"] = torch.empty(pl.n_act, **bf)
+        if "hcl" not in self._saved:
+            self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)
+
+    # ------------------------------------------------------------------ kernels
+    def _gemm(self, st: dict, bufs: Dict[str, torch.Tensor], adj: bool, add: Optional[torch.Tensor] = None) -> None:
+        op = self.ops[st["op"] + ("_adj" if adj else "")]
+        A, dst = bufs[st["src"]], bufs[st["dst"]]
+        if "scatter" in st:
+            spec: ScatterSpec = st["scatter"]
+            if st.get("peer_dst") and self.world > 1:
+                sym = self.sym_S1 if st["dst"] == "S1" else self.sym_T1
+                ptrs = sym.peer_ptrs()
+            else:
+                ptrs = [dst.data_ptr()] * max(self.world, 1)
+            self._C.dft_gemm(A, st["M"], st["K"], st["lda"], op, st["N"], spec.epi(), ptrs, None, 0, 0)
+        else:
+            epi = [0, 0, st["ldc"], 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 0]
+            self._C.dft_gemm(A, st["M"], st["K"], st["lda"], op, st["N"], epi, [dst.data_ptr()], add,
+                             st["ldc"] if add is not None else 0, 0)
+        if st.get("barrier_after"):
+            self.barrier()
+
+    def _spectral_chain(self, src, dst, block: int, adj: bool, add=None) -> None:
+        """src (engine layout) -> truncated spectrum -> channel mix -> dst (engine layout)."""
+        pl = self.plan
+        ws = self.ws
+        s3 = self._saved["S3"][block] if (self._train_bufs_ready and not self._eval_mode) else ws["S3w"]
+        bufs = {"src": src, "Z1": ws["Z1U"], "S1": ws["S1"], "S2": ws["S2"],
+                "S3": ws["S3w"] if adj else s3, "S4": ws["S4"], "T2": ws["T2"], "T1": ws["T1"],
+                "U": ws["Z1U"], "dst": dst}
+        R = self._seg(f"blocks.{block}.spectral")
+        for st in self.chain_desc:
+            if st["name"] == "mix":
+                if adj:
+                    gR = self._seg(f"blocks.{block}.spectral", self.grad_flat)
+                    self._C.spectral_mix_bwd(s3, R, bufs["S3"], bufs["S4"], gR, getattr(self, "_acc", False), pl.B, pl.C, pl.Q)
+                else:
+                    self._C.spectral_mix_fwd(bufs["S3"], R, bufs["S4"], pl.B, pl.C, pl.Q)
+            else:
+                self._gemm(st, bufs, adj, add if st["name"] == "iG1a" else None)
+
+    # ------------------------------------------------------------------ projection head (torch, v1)
+    def _head_forward(self, hcl: torch.Tensor) -> torch.Tensor:
+        pl = self.plan
+        W3, b3 = self._seg("linear3.W").to(torch.bfloat16), self._seg("linear3.b").to(torch.bfloat16)
+        W4, b4 = self._seg("linear4.W").to(torch.bfloat16), self._seg("linear4.b")
+        out = torch.empty(pl.npos, device=self.device, dtype=torch.float32)
+        step = 1 << 22
+        for a in range(0, pl.npos, step):
+            b = min(pl.npos, a + step)
+            hid = F.gelu(torch.addmm(b3, hcl[a:b, :pl.C], W3.t()))
+            out[a:b] = (hid @ W4.t()).float().squeeze(1) + b4
+        return out
+
+    def _head_backward(self, hcl: torch.Tensor, dout: torch.Tensor, gcl: torch.Tensor) -> None:
+        pl = self.plan
+        names = ["linear3.W", "linear3.b", "linear4.W", "linear4.b"]
+        leaves = [self._seg(n).detach().clone().requires_grad_() for n in names]
+        step = 1 << 22
+        for a in range(0, pl.npos, step):
+            b = min(pl.npos, a + step)
+            with torch.enable_grad():
+                xin = hcl[a:b, :pl.C].detach().requires_grad_()
+                W3, b3, W4, b4 = leaves
+                hid = F.gelu(torch.addmm(b3.to(torch.bfloat16), xin, W3.to(torch.bfloat16).t()))
+                o = (hid @ W4.to(torch.bfloat16).t()).float().squeeze(1) + b4
+                o.backward(dout[a:b])
+            gcl[a:b, :pl.C] = xin.grad
+        for n, leaf in zip(names, leaves):
+            self._seg(n, self.grad_flat).add_(leaf.grad)
+
+    # ------------------------------------------------------------------ forward / backward
+    _eval_mode = False
+
+    def _lift_dims(self) -> List[int]:
+        pl = self.plan
+        return [pl.B, pl.Cin, pl.Tin, pl.C, pl.T, pl.X, pl.Yl, pl.Z]
+
+    def _forward(self, x: torch.Tensor, save: bool) -> torch.Tensor:
+        pl, C_ = self.plan, self._C
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        expect = (pl.B, pl.Cin, pl.X, pl.Yl, pl.Z, pl.Tin)
+        if tuple(x.shape) != expect:
+            raise ValueError(f"expected local input {expect}, got {tuple(x.shape)}")
+        self._eval_mode = not save
+        if save:
+            self._ensure_train_buffers()
+            hs, pres = self._saved["h"], self._saved["pre"]
+        else:
+            self._ensure_eval_buffers()
+            hs = [self.ws["eval_h"][k % 2] for k in range(self.num_blocks)]
+            pres = [self.ws["eval_pre"]] * self.num_blocks
+        hcl = self._saved["hcl"]
+        C_.lift_fwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
+                    self._seg("linear2.b"), hs[0], self._lift_dims())
+        for k in range(self.num_blocks):
+            last = k == self.num_blocks - 1
+            self._spectral_chain(hs[k], pres[k], k, adj=False)
+            C_.bypass_gelu_fwd(hs[k], pres[k], self._seg(f"blocks.{k}.linear.W"),
+                               None if last else hs[k + 1], hcl if last else None, pl.CP,
+                               pl.B, pl.C, pl.S, save)
+        out = self._head_forward(hcl)
+        return out.view(pl.B, 1, pl.X, pl.Yl, pl.T, pl.Z).permute(0, 1, 2, 3, 5, 4).contiguous()
+
+    def _backward(self, x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+        pl, C_ = self.plan, self._C
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        self._eval_mode = False
+        hs, pres, hcl = self._saved["h"], self._saved["pre"], self._saved["hcl"]
+        g, dhb, gcl = self.ws["g"], self.ws["dhb"], self.ws["gcl"]
+        if not (self.accumulate_grads and self.theta.grad is self.grad_flat):
+            # spectral gradients are overwritten by the mix backward; only the small,
+            # atomically accumulated segment needs clearing
+            self.grad_flat[:pl.n_small].zero_()
+        self._acc = bool(self.accumulate_grads and self.theta.grad is self.grad_flat)
+        dout = dy.reshape(pl.B, pl.X, pl.Yl, pl.Z, pl.T).permute(0, 1, 2, 4, 3).contiguous().view(-1).float()
+        self._head_backward(hcl, dout, gcl)
+        for k in reversed(range(self.num_blocks)):
+            last = k == self.num_blocks - 1
+            Wb = self._seg(f"blocks.{k}.linear.W")
+            # dpre overwrites pre (same thread reads then writes each element)
+            C_.bypass_gelu_bwd(None if last else g, gcl if last else None, pl.CP, pres[k], Wb, pres[k], dhb,
+                               pl.B, pl.C, pl.S)
+            gW = self._seg(f"blocks.{k}.linear.W", self.grad_flat)
+            for b in range(pl.B):
+                sl = slice(b * pl.C * pl.S, (b + 1) * pl.C * pl.S)
+                C_.kreduce_gemm(pres[k][sl], pl.S, pl.C, hs[k][sl], pl.S, pl.C, pl.S, gW)
+            self._spectral_chain(pres[k], g, k, adj=True, add=dhb)
+        C_.lift_bwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
+                    self._seg("linear2.b"), g, self._seg("linear1.W", self.grad_flat),
+                    self._seg("linear1.b", self.grad_flat), self._seg("linear2.W", self.grad_flat),
+                    self._seg("linear2.b", self.grad_flat), self._lift_dims())
+        self._sync_small_grads()
+        self.theta.grad = self.grad_flat
+        return self.grad_flat
+
+    def _sync_small_grads(self) -> None:
+        """Sum the replicated pointwise-weight gradients over the pencil (the SumReduce side
+        of the reference's BroadcastedLinear, once per step instead of per layer)."""
+        if self.world <= 1:
+            return
+        pl = self.plan
+        small = self.grad_flat[:pl.n_small]
+        if self.use_p2p:
+            stage = self.sym_small.view([pl.n_small], torch.float32)
+            self.barrier()                       # previous readers are done with the staging buffer
+            stage.copy_(small)
+            self.barrier()                       # every rank's contribution is visible
+            self._C.p2p_allreduce_small(self.sym_small.peer_ptrs(), small, pl.n_small, self.rank)
+        else:
+            dist.all_reduce(small, group=self.P_x.group)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _FusedFn.apply(x, self.theta, self)
+
+    # ------------------------------------------------------------------ canonical state <-> engine
+    def engine_state_to_global(self, to_all: bool = False):
+        """Canonical (partition independent) state on rank 0 / all ranks (CPU tensors)."""
+        pl = self.plan
+        mine = {}
+        for name, (off, shape) in pl.segments.items():
+            t = self._seg(name).detach().cpu()
+            if name.endswith(".spectral"):
+                # native [i, o, kzl, mt, KY, KX, 2] -> global slab [i, o, KX, KY, kzl, mt]
+                w = torch.view_as_complex(t.view(pl.C, pl.C, pl.kzl, pl.mt, pl.KY, pl.KX, 2).contiguous())
+                mine[name] = (pl.kz_off, w.permute(0, 1, 5, 4, 2, 3).contiguous())
+            elif self.rank == 0:
+                key, tt = name, t
+                if name.endswith(".b"):
+                    b_shape = [1] * 6
+                    b_shape[-1 if name.startswith("linear1") else 1] = t.numel()
+                    tt = t.view(b_shape)
+                mine[key] = tt
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=self.P_x.group)
+        else:
+            gathered = [mine]
+        if not (to_all or self.rank == 0):
+            return None
+        out = {}
+        for part in gathered:
+            for k, v in part.items():
+                if k.endswith(".spectral"):
+                    kz0, w = v
+                    if k not in out:
+                        out[k] = torch.zeros(pl.C, pl.C, pl.KX, pl.KY, pl.KZ, pl.mt, dtype=torch.complex64)
+                    out[k][:, :, :, :, kz0:kz0 + w.shape[4], :] = w
+                else:
+                    out[k] = v
+        for k in range(self.num_blocks):          # key parity with the portable backend
+            out.setdefault(f"blocks.{k}.linear.b", torch.zeros(1, pl.C, 1, 1, 1, 1))
+        return out
+
+    def engine_state_from_global(self, state) -> None:
+        pl = self.plan
+        with torch.no_grad():
+            for name, (off, shape) in pl.segments.items():
+                if name not in state:
+                    continue
+                src = state[name]
+                if name.endswith(".spectral"):
+                    w = src[:, :, :, :, pl.kz_off:pl.kz_off + pl.kzl, :].to(torch.complex64)
+                    w = torch.view_as_real(w.permute(0, 1, 4, 5, 3, 2).contiguous())   # [i,o,kzl,mt,KY,KX,2]
+                    self._seg(name).copy_(w.reshape(shape).to(self.device))
+                else:
+                    self._seg(name).copy_(src.reshape(shape).to(self.device, torch.float32))
+
+
+# =====================================================================================
+# optimizer
+# =====================================================================================
+
+class FusedAdam:
+    """Adam on the engine's flat parameter buffer with one fused kernel launch per step
+    (``csrc/optim.cu``); semantics of ``torch.optim.Adam`` (L2 ``weight_decay``)."""
+
+    def __init__(self, model: FusedDistributedFNO, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(model.theta.data)
+        self.v = torch.zeros_like(model.theta.data)
+        self.step_count = 0
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        if set_to_none:
+            self.model.theta.grad = None
+        elif self.model.theta.grad is not None:
+            self.model.theta.grad.zero_()
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        g = self.model.theta.grad
+        if g is None:
+            return
+        self.step_count += 1
+        self.model._C.adam_step(self.model.theta.data, g.contiguous(), self.m, self.v, self.lr, self.betas[0],
+                                self.betas[1], self.eps, self.weight_decay, self.step_count, grad_scale)
+
+    def state_dict(self):
+        return {"m": self.m, "v": self.v, "step": self.step_count, "lr": self.lr, "betas": self.betas,
+                "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd) -> None:
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
+        self.step_count = int(sd["step"])
+        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
