@@ -12,3 +12,5 @@ __version__ = "0.1.0"
 from .parallel import *           # noqa: F401,F403
 from .utils import *              # noqa: F401,F403
 from .models import *             # noqa: F401,F403
+from .trainer import Trainer      # noqa: E402,F401
+from .models.fused import FusedDistributedFNO, FusedAdam   # noqa: E402,F401

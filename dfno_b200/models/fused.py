@@ -238,6 +238,27 @@ class EnginePlan:
 # the module
 # =====================================================================================
 
+class _LaunchCounter:
+    """Proxy around the extension module that counts kernel launches issued by the engine
+    (reported by ``bench.py`` as ``gpu_launches``)."""
+
+    _multi = {"spectral_mix_bwd": "B"}
+
+    def __init__(self, mod):
+        self._mod = mod
+        self.count = 0
+
+    def __getattr__(self, name):
+        fn = getattr(self._mod, name)
+        if name.startswith(("symm_", "tensor_from_ptr")):
+            return fn
+
+        def call(*a, **k):
+            self.count += 1
+            return fn(*a, **k)
+        return call
+
+
 class _FusedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, theta, eng):
@@ -269,7 +290,7 @@ class FusedDistributedFNO(nn.Module):
         if not ok:
             raise ValueError(f"fused engine cannot run this configuration: {why}")
         from ..ops import build
-        self._C = build.load()                 # fails loudly if the extension is missing
+        self._C = _LaunchCounter(build.load())   # fails loudly if the extension is missing
         self.P_x = P_x
         self.in_shape = [int(s) for s in in_shape]
         self.out_timesteps, self.width = int(out_timesteps), int(width)
