@@ -25,7 +25,8 @@ void check(const char* err, const char* what) {
 // epi = [mode, out_fp32, ldc, nrl, R0..R3, SR0..SR3, J0, J1, SJ0, SJ1, peer_sel, peer_lvl, peer_div, base_off]
 void dft_gemm(const at::Tensor& A, int64_t M, int64_t K, int64_t lda, const at::Tensor& Bmat, int64_t N,
               const std::vector<int64_t>& epi, const std::vector<int64_t>& peer_ptrs,
-              const c10::optional<at::Tensor>& add_src, int64_t ld_add, int64_t max_ctas) {
+              const c10::optional<at::Tensor>& add_src, int64_t ld_add, int64_t max_ctas,
+              const c10::optional<at::Tensor>& v0, const c10::optional<at::Tensor>& v1, double s0) {
   TORCH_CHECK(A.is_cuda() && A.scalar_type() == at::kBFloat16, "A must be a CUDA bf16 tensor");
   TORCH_CHECK(Bmat.is_cuda() && Bmat.scalar_type() == at::kBFloat16 && Bmat.dim() == 2 && Bmat.is_contiguous(),
               "operator must be a contiguous CUDA bf16 [n_pad, k_pad] tensor");
@@ -50,6 +51,14 @@ void dft_gemm(const at::Tensor& A, int64_t M, int64_t K, int64_t lda, const at::
     TORCH_CHECK(add_src->scalar_type() == at::kBFloat16, "add_src must be bf16");
     e.add_src = add_src->data_ptr();
   }
+  e.v0 = nullptr; e.v1 = nullptr; e.s0 = static_cast<float>(s0);
+  if (e.mode == dfno::EPI_HEAD) {
+    TORCH_CHECK(v0.has_value() && v1.has_value(), "EPI_HEAD needs the hidden bias and output weights");
+    TORCH_CHECK(v0->scalar_type() == at::kFloat && v1->scalar_type() == at::kFloat && v0->is_contiguous() &&
+                v1->is_contiguous() && v0->numel() >= N && v1->numel() >= N + 1 && N < 255, "bad head vectors");
+    TORCH_CHECK(e.nrl >= 1 && e.nrl <= 4, "bad head row digits");
+    e.v0 = v0->data_ptr<float>(); e.v1 = v1->data_ptr<float>();
+  }
   if (e.mode == dfno::EPI_PAIR_SCATTER) {
     TORCH_CHECK(N % 2 == 0 && e.J[0] > 0 && e.nrl >= 1 && e.nrl <= 4, "bad scatter descriptor");
     for (int i = 0; i + 1 < e.nrl; ++i) TORCH_CHECK(e.R[i] > 0, "row radix must be positive");
@@ -70,7 +79,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dft_gemm", &dft_gemm, "resident-operator GEMM on tcgen05 (see dft_gemm_sm100.cu)",
         py::arg("A"), py::arg("M"), py::arg("K"), py::arg("lda"), py::arg("Bmat"), py::arg("N"),
         py::arg("epi"), py::arg("peer_ptrs"), py::arg("add_src") = c10::nullopt, py::arg("ld_add") = 0,
-        py::arg("max_ctas") = 0);
+        py::arg("max_ctas") = 0, py::arg("v0") = c10::nullopt, py::arg("v1") = c10::nullopt, py::arg("s0") = 0.0);
   register_ops(m);
   register_symm(m);
 }

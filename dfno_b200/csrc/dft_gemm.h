@@ -5,7 +5,7 @@
 
 namespace dfno {
 
-enum EpiMode { EPI_ROWMAJOR = 0, EPI_PAIR_SCATTER = 1 };
+enum EpiMode { EPI_ROWMAJOR = 0, EPI_PAIR_SCATTER = 1, EPI_HEAD = 2 };
 enum PeerSel { PEER_NONE = 0, PEER_BY_ROW = 1, PEER_BY_COL = 2 };
 
 // Output addressing of the epilogue.  All strides/offsets are in *elements of the output
@@ -17,6 +17,9 @@ enum PeerSel { PEER_NONE = 0, PEER_BY_ROW = 1, PEER_BY_COL = 2 };
 //                      with strides SJ[].  One digit (a row digit, or j itself) may select the
 //                      destination peer: peer = digit / peer_div, and digit % peer_div is used
 //                      for addressing inside that peer's buffer.
+//   EPI_HEAD         : projection head: out[addr(row)] = s0 + sum_j v1[j] * gelu(acc[row, j] + v0[j])
+//                      (fp32 out; addr(row) from the row digits), i.e. linear3 -> gelu -> linear4
+//                      without ever materialising the 128-channel intermediate.
 struct EpiParams {
   int mode;
   int out_fp32;
@@ -34,6 +37,9 @@ struct EpiParams {
   int peer_div;
   long long base_off;
   void* peers[8];
+  const float* v0;       // EPI_HEAD: bias of the hidden layer   [N]
+  const float* v1;       // EPI_HEAD: weights of the output layer [N]
+  float s0;              // EPI_HEAD: output bias
 };
 
 struct GemmParams {

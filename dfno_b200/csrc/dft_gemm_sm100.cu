@@ -55,6 +55,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty = tfull + 2;               // [2]        epilogue -> MMA
   uint64_t* bfull = tempty + 2;               // [1]        B resident
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bfull + 1);
+  long long* s_coloff = reinterpret_cast<long long*>(bars + 16);        // [128] pair -> element offset
+  float* s_vec = reinterpret_cast<float*>(s_coloff + 128);              // [512] EPI_HEAD vectors
+  uint8_t* s_colpeer = reinterpret_cast<uint8_t*>(s_vec + 512);         // [128] pair -> peer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,6 +134,23 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int r_in_tile = q * 32 + lane;
     uint32_t acc = 0, acc_ph = 0;
     const int npairs = p.N >> 1;
+    {
+      // per-CTA lookup tables (epilogue warps only; named barrier 1, 128 threads)
+      const int et = threadIdx.x - 64;
+      if (p.epi.mode == EPI_PAIR_SCATTER) {
+        for (int j = et; j < npairs && j < 128; j += 128) {
+          int jj = j, peer = 0;
+          if (p.epi.peer_sel == PEER_BY_COL) { peer = jj / p.epi.peer_div; jj -= peer * p.epi.peer_div; }
+          const int j0 = jj % p.epi.J[0], j1 = jj / p.epi.J[0];
+          s_coloff[j] = j0 * p.epi.SJ[0] + j1 * p.epi.SJ[1];
+          s_colpeer[j] = static_cast<uint8_t>(peer);
+        }
+      } else if (p.epi.mode == EPI_HEAD) {
+        for (int j = et; j < p.N; j += 128) { s_vec[j] = p.epi.v0[j]; s_vec[256 + j] = p.epi.v1[j]; }
+        if (et == 0) s_vec[511] = p.epi.v1[p.N];          // output bias stored right after the weights
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long row = static_cast<long long>(tile) * kTileM + r_in_tile;
       const bool row_ok = row < p.M;
@@ -189,18 +209,18 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-      } else {
+      } else if (p.epi.mode == EPI_PAIR_SCATTER) {
         // ---- pair scatter: (re, im) pairs to a mixed-radix address, possibly on a peer GPU
         long long roff = p.epi.base_off;
         int rpeer = 0;
         {
-          long long r = row;
+          uint32_t r = static_cast<uint32_t>(row_ok ? row : 0);
 #pragma unroll
           for (int l = 0; l < 4; ++l) {
             if (l < p.epi.nrl) {
-              const int radix = p.epi.R[l];
-              int d = (l == p.epi.nrl - 1) ? static_cast<int>(r) : static_cast<int>(r % radix);
-              r /= radix;
+              const uint32_t radix = static_cast<uint32_t>(p.epi.R[l]);
+              uint32_t d = r;
+              if (l != p.epi.nrl - 1) { const uint32_t qq = r / radix; d = r - qq * radix; r = qq; }
               if (p.epi.peer_sel == PEER_BY_ROW && l == p.epi.peer_lvl) {
                 rpeer = d / p.epi.peer_div;
                 d -= rpeer * p.epi.peer_div;
@@ -209,6 +229,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+        __nv_bfloat16* const rbase = reinterpret_cast<__nv_bfloat16*>(p.epi.peers[rpeer]) + roff;
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
@@ -216,22 +237,45 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (!row_ok) continue;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            int j = (c0 >> 1) + i;
+            const int j = (c0 >> 1) + i;
             if (j < npairs) {
-              int peer = rpeer;
-              if (p.epi.peer_sel == PEER_BY_COL) {
-                peer = j / p.epi.peer_div;
-                j -= peer * p.epi.peer_div;
-              }
-              const int j0 = j % p.epi.J[0];
-              const int j1 = j / p.epi.J[0];
-              const long long off = roff + j0 * p.epi.SJ[0] + j1 * p.epi.SJ[1];
-              uint32_t* o = reinterpret_cast<uint32_t*>(
-                  reinterpret_cast<__nv_bfloat16*>(p.epi.peers[peer]) + off);
-              *o = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              __nv_bfloat16* base = rbase;
+              if (p.epi.peer_sel == PEER_BY_COL)
+                base = reinterpret_cast<__nv_bfloat16*>(p.epi.peers[s_colpeer[j]]) + roff;
+              *reinterpret_cast<uint32_t*>(base + s_coloff[j]) =
+                  pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
             }
           }
         }
+      } else {
+        // ---- projection head: out = s0 + sum_j v1[j] * gelu(acc[j] + v0[j])
+        long long roff = p.epi.base_off;
+        {
+          uint32_t r = static_cast<uint32_t>(row_ok ? row : 0);
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            if (l < p.epi.nrl) {
+              const uint32_t radix = static_cast<uint32_t>(p.epi.R[l]);
+              uint32_t d = r;
+              if (l != p.epi.nrl - 1) { const uint32_t qq = r / radix; d = r - qq * radix; r = qq; }
+              roff += static_cast<long long>(d) * p.epi.SR[l];
+            }
+          }
+        }
+        float acc_out = s_vec[511];
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (c0 + i < p.N) {
+              const float pre = __uint_as_float(v[i]) + s_vec[c0 + i];
+              acc_out = fmaf(s_vec[256 + c0 + i], gelu_erf(pre), acc_out);
+            }
+          }
+        }
+        if (row_ok) reinterpret_cast<float*>(p.epi.peers[0])[roff] = acc_out;
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tcgen05_fence_before();
@@ -272,11 +316,11 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   const int kblocks = p.k_pad / kBlockK;
   L.b_bytes = static_cast<uint32_t>(kblocks) * p.n_pad * 128;
   L.a_tile_bytes = static_cast<uint32_t>(kblocks) * kTileM * 128;
-  const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 4096 /*barriers + tables*/;
   if (L.b_bytes + 2 * L.a_tile_bytes > budget) return "operator too large for shared memory";
   L.stages = (budget - L.b_bytes) / L.a_tile_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
-  uint32_t smem_bytes = L.b_bytes + L.stages * L.a_tile_bytes + 256;
+  uint32_t smem_bytes = L.b_bytes + L.stages * L.a_tile_bytes + 4096;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;     // force one CTA per SM (TMEM: 512 cols)
 
   CUtensorMap tmA, tmB;

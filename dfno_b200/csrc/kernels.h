@@ -46,4 +46,10 @@ const char* p2p_allreduce_small(float* const* peer_bufs, float* out, long long n
 const char* kreduce_gemm(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, long long K,
                          float* D, long long ldd, int num_sms, cudaStream_t s);
 
+// backward of the projection head (head_bwd_sm100.cu).  dout is read at the mixed-radix address
+// of each row (public [B,1,X,Y,Z,T] layout); gradients are accumulated with atomics.
+const char* head_bwd(const void* hcl, long long npos, int C, int CP, const void* W3pad, const void* W3Tpad,
+                     const float* b3, const float* W4, const float* dout, int nrl, const int* R, const long long* SR,
+                     void* gcl, float* gW3, float* gb3, float* gW4, float* gb4, int num_sms, cudaStream_t stream);
+
 }  // namespace dfno

@@ -119,6 +119,21 @@ void kreduce_gemm(const at::Tensor& A, int64_t lda, int64_t Ma, const at::Tensor
                            D.stride(0), sm_count(), cur_stream()), "kreduce_gemm");
 }
 
+void head_bwd(const at::Tensor& hcl, int64_t npos, int64_t C, int64_t CP, const at::Tensor& W3pad,
+              const at::Tensor& W3Tpad, const at::Tensor& b3, const at::Tensor& W4, const at::Tensor& dout,
+              const std::vector<int64_t>& radices, const std::vector<int64_t>& strides, at::Tensor& gcl,
+              at::Tensor& gW3, at::Tensor& gb3, at::Tensor& gW4, at::Tensor& gb4) {
+  TORCH_CHECK(radices.size() == strides.size() && !radices.empty() && radices.size() <= 4, "1..4 row digits");
+  TORCH_CHECK(W3pad.dim() == 2 && W3pad.size(0) == 128 && W3pad.size(1) == 64 && W3pad.is_contiguous(), "W3pad [128,64]");
+  TORCH_CHECK(W3Tpad.dim() == 2 && W3Tpad.size(0) == 32 && W3Tpad.size(1) == 128 && W3Tpad.is_contiguous(), "W3Tpad [32,128]");
+  c10::cuda::CUDAGuard guard(hcl.device());
+  int R[4]; long long SR[4];
+  for (size_t i = 0; i < 4; ++i) { R[i] = i < radices.size() ? static_cast<int>(radices[i]) : 1; SR[i] = i < strides.size() ? strides[i] : 0; }
+  check(dfno::head_bwd(bptr(hcl), npos, static_cast<int>(C), static_cast<int>(CP), bptr(W3pad), bptr(W3Tpad), fptr(b3),
+                       fptr(W4), fptr(dout), static_cast<int>(radices.size()), R, SR, bptr(gcl), fptr_mut(gW3),
+                       fptr_mut(gb3), fptr_mut(gW4), fptr_mut(gb4), sm_count(), cur_stream()), "head_bwd");
+}
+
 }  // namespace
 
 void register_ops(pybind11::module& m) {
@@ -132,4 +147,5 @@ void register_ops(pybind11::module& m) {
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_allreduce_small", &p2p_allreduce_small);
   m.def("kreduce_gemm", &kreduce_gemm);
+  m.def("head_bwd", &head_bwd);
 }

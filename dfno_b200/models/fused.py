@@ -435,35 +435,48 @@ class FusedDistributedFNO(nn.Module):
             else:
                 self._gemm(st, bufs, adj, add if st["name"] == "iG1a" else None)
 
-    # ------------------------------------------------------------------ projection head (torch, v1)
-    def _head_forward(self, hcl: torch.Tensor) -> torch.Tensor:
+    # ------------------------------------------------------------------ projection head
+    def _head_operators(self):
         pl = self.plan
-        W3, b3 = self._seg("linear3.W").to(torch.bfloat16), self._seg("linear3.b").to(torch.bfloat16)
-        W4, b4 = self._seg("linear4.W").to(torch.bfloat16), self._seg("linear4.b")
-        out = torch.empty(pl.npos, device=self.device, dtype=torch.float32)
-        step = 1 << 22
-        for a in range(0, pl.npos, step):
-            b = min(pl.npos, a + step)
-            hid = F.gelu(torch.addmm(b3, hcl[a:b, :pl.C], W3.t()))
-            out[a:b] = (hid @ W4.t()).float().squeeze(1) + b4
+        W3 = self._seg("linear3.W")                                   # [H, C] fp32
+        w3 = torch.zeros(pl.H, 64, device=self.device, dtype=torch.bfloat16)
+        w3[:, :pl.C] = W3.to(torch.bfloat16)
+        w3t = torch.zeros(32, pl.H, device=self.device, dtype=torch.bfloat16)
+        w3t[:pl.C] = W3.t().to(torch.bfloat16)
+        return w3, w3t
+
+    def _w4b4(self) -> torch.Tensor:
+        """``[W4 (H), b4 (1)]`` -- adjacent in the flat parameter buffer by construction."""
+        off, _ = self.plan.segments["linear4.W"]
+        assert self.plan.segments["linear4.b"][0] == off + self.plan.H
+        return self.theta.data[off:off + self.plan.H + 1]
+
+    def _head_row_digits(self):
+        """Row (b, x, y, t, z) of the engine layout -> element offset in the public
+        ``[B, 1, X, Y, Z, T]`` output: digits innermost first."""
+        pl = self.plan
+        return [pl.Z, pl.T, pl.B * pl.X * pl.Yl], [pl.T, 1, pl.Z * pl.T]
+
+    def _head_forward(self, hcl: torch.Tensor) -> torch.Tensor:
+        """linear3 -> gelu -> linear4 in the epilogue of one tcgen05 GEMM (EPI_HEAD)."""
+        pl = self.plan
+        w3, _ = self._head_operators()
+        out = torch.empty(pl.B, 1, pl.X, pl.Yl, pl.Z, pl.T, device=self.device, dtype=torch.float32)
+        R, SR = self._head_row_digits()
+        epi = [2, 1, 0, 3, *R, 1, *SR, 0, 1, 1, 0, 0, 0, 0, 1, 0]
+        self._C.dft_gemm(hcl, pl.npos, pl.C, pl.CP, w3, pl.H, epi, [out.data_ptr()], None, 0, 0,
+                         self._seg("linear3.b"), self._w4b4(), 0.0)
         return out
 
-    def _head_backward(self, hcl: torch.Tensor, dout: torch.Tensor, gcl: torch.Tensor) -> None:
+    def _head_backward(self, hcl: torch.Tensor, dy: torch.Tensor, gcl: torch.Tensor) -> None:
         pl = self.plan
-        names = ["linear3.W", "linear3.b", "linear4.W", "linear4.b"]
-        leaves = [self._seg(n).detach().clone().requires_grad_() for n in names]
-        step = 1 << 22
-        for a in range(0, pl.npos, step):
-            b = min(pl.npos, a + step)
-            with torch.enable_grad():
-                xin = hcl[a:b, :pl.C].detach().requires_grad_()
-                W3, b3, W4, b4 = leaves
-                hid = F.gelu(torch.addmm(b3.to(torch.bfloat16), xin, W3.to(torch.bfloat16).t()))
-                o = (hid @ W4.to(torch.bfloat16).t()).float().squeeze(1) + b4
-                o.backward(dout[a:b])
-            gcl[a:b, :pl.C] = xin.grad
-        for n, leaf in zip(names, leaves):
-            self._seg(n, self.grad_flat).add_(leaf.grad)
+        w3, w3t = self._head_operators()
+        R, SR = self._head_row_digits()
+        g = self.grad_flat
+        self._C.head_bwd(hcl, pl.npos, pl.C, pl.CP, w3, w3t, self._seg("linear3.b"),
+                         self._seg("linear4.W").view(-1), dy, R, SR, gcl,
+                         self._seg("linear3.W", g), self._seg("linear3.b", g),
+                         self._seg("linear4.W", g).view(-1), self._seg("linear4.b", g))
 
     # ------------------------------------------------------------------ forward / backward
     _eval_mode = False
@@ -497,8 +510,7 @@ class FusedDistributedFNO(nn.Module):
             C_.bypass_gelu_fwd(hs[k], pres[k], self._seg(f"blocks.{k}.linear.W"),
                                None if last else hs[k + 1], hcl if last else None, pl.CP,
                                pl.B, pl.C, pl.S, save)
-        out = self._head_forward(hcl)
-        return out.view(pl.B, 1, pl.X, pl.Yl, pl.T, pl.Z).permute(0, 1, 2, 3, 5, 4).contiguous()
+        return self._head_forward(hcl)
 
     def _backward(self, x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
         pl, C_ = self.plan, self._C
@@ -513,8 +525,7 @@ class FusedDistributedFNO(nn.Module):
             # atomically accumulated segment needs clearing
             self.grad_flat[:pl.n_small].zero_()
         self._acc = bool(self.accumulate_grads and self.theta.grad is self.grad_flat)
-        dout = dy.reshape(pl.B, pl.X, pl.Yl, pl.Z, pl.T).permute(0, 1, 2, 4, 3).contiguous().view(-1).float()
-        self._head_backward(hcl, dout, gcl)
+        self._head_backward(hcl, dy.contiguous().float(), gcl)
         for k in reversed(range(self.num_blocks)):
             last = k == self.num_blocks - 1
             Wb = self._seg(f"blocks.{k}.linear.W")
