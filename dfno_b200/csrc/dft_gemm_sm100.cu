@@ -40,6 +40,8 @@ struct SmemLayout {
   uint32_t b_bytes;       // kblocks * n_pad * 128
   uint32_t a_tile_bytes;  // kblocks * 16384
   uint32_t stages;
+  uint32_t stage_off;     // byte offset of the epilogue staging area (0 = none)
+  uint32_t stage_pitch;   // bytes per staged row (fp32 row + 16 B pad)
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -158,7 +160,54 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_pad;
 
-      if (p.epi.mode == EPI_ROWMAJOR) {
+      if (p.epi.mode == EPI_ROWMAJOR && L.stage_off != 0) {
+        // ---- coalesced row-major store: TMEM -> fp32 staging rows in smem (one 32-row slab
+        // per warp) -> each half-warp / quarter-warp writes whole rows contiguously
+        uint8_t* slab = smem + L.stage_off + q * 32 * L.stage_pitch;
+        float* myrow = reinterpret_cast<float*>(slab + lane * L.stage_pitch);
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(myrow + c0)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        __syncwarp();
+        const int vec_per_row = p.N >> 3;                       // 8 outputs (16 B of bf16) per lane
+        const int rows_per_it = 32 / vec_per_row;               // N = 128 -> 16 lanes per row, 2 rows / instr
+        const int lr = lane / vec_per_row, lc = lane % vec_per_row;
+        const long long row0 = static_cast<long long>(tile) * kTileM + q * 32;
+        if (lr < rows_per_it) {
+          for (int rr = lr; rr < 32; rr += rows_per_it) {
+            const long long grow = row0 + rr;
+            if (grow >= p.M) break;
+            const float* srow = reinterpret_cast<const float*>(slab + rr * L.stage_pitch) + lc * 8;
+            float4 f0 = reinterpret_cast<const float4*>(srow)[0];
+            float4 f1 = reinterpret_cast<const float4*>(srow)[1];
+            if (p.epi.add_src != nullptr) {
+              const uint4 a = *reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) + grow * p.epi.ld_add + lc * 8);
+              float2 t;
+              t = unpack_bf16x2(a.x); f0.x += t.x; f0.y += t.y;
+              t = unpack_bf16x2(a.y); f0.z += t.x; f0.w += t.y;
+              t = unpack_bf16x2(a.z); f1.x += t.x; f1.y += t.y;
+              t = unpack_bf16x2(a.w); f1.z += t.x; f1.w += t.y;
+            }
+            if (p.epi.out_fp32) {
+              float* o = reinterpret_cast<float*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8;
+              reinterpret_cast<float4*>(o)[0] = f0;
+              reinterpret_cast<float4*>(o)[1] = f1;
+            } else {
+              uint4 u;
+              u.x = pack_bf16x2(f0.x, f0.y); u.y = pack_bf16x2(f0.z, f0.w);
+              u.z = pack_bf16x2(f1.x, f1.y); u.w = pack_bf16x2(f1.z, f1.w);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = u;
+            }
+          }
+        }
+        __syncwarp();
+      } else if (p.epi.mode == EPI_ROWMAJOR) {
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
@@ -318,9 +367,19 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   L.a_tile_bytes = static_cast<uint32_t>(kblocks) * kTileM * 128;
   const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 4096 /*barriers + tables*/;
   if (L.b_bytes + 2 * L.a_tile_bytes > budget) return "operator too large for shared memory";
-  L.stages = (budget - L.b_bytes) / L.a_tile_bytes;
+  // coalesced row-major epilogue: needs N to be a multiple of 8 dividing 256 and aligned rows
+  L.stage_off = 0; L.stage_pitch = 0;
+  uint32_t stage_total = 0;
+  if (p.epi.mode == EPI_ROWMAJOR && p.epi.vec_ok && p.N % 8 == 0 && (p.N == 8 || p.N == 16 || p.N == 32 ||
+      p.N == 64 || p.N == 128 || p.N == 256)) {
+    const uint32_t pitch = p.N * 4 + 16;
+    const uint32_t need = 4 * 32 * pitch;
+    if (L.b_bytes + 2 * L.a_tile_bytes + need <= budget) { L.stage_pitch = pitch; stage_total = need; }
+  }
+  L.stages = (budget - L.b_bytes - stage_total) / L.a_tile_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
-  uint32_t smem_bytes = L.b_bytes + L.stages * L.a_tile_bytes + 4096;
+  if (stage_total) L.stage_off = L.b_bytes + L.stages * L.a_tile_bytes + 4096;
+  uint32_t smem_bytes = L.b_bytes + L.stages * L.a_tile_bytes + 4096 + stage_total;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;     // force one CTA per SM (TMEM: 512 cols)
 
   CUtensorMap tmA, tmB;

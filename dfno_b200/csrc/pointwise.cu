@@ -241,7 +241,10 @@ bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __res
       const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(h + base + i * S));
       h0[i] = v.x; h1[i] = v.y;
     }
-#pragma unroll 4
+    // channels-last rows (for the projection head) are assembled in registers and written as
+    // 8-byte vectors: two rows of cl_pitch bf16 per thread
+    uint32_t cl0[C / 2 + 1], cl1[C / 2 + 1];
+#pragma unroll
     for (int o = 0; o < C; ++o) {
       const float2 s = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(spec_pre + base + o * S));
       float a0 = s.x, a1 = s.y;
@@ -255,9 +258,24 @@ bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __res
       const float y0 = gelu_erf(a0), y1 = gelu_erf(a1);
       if (out) *reinterpret_cast<uint32_t*>(out + base + o * S) = pack_bf16x2(y0, y1);
       if (out_cl) {
-        const long long r = (b * S + 2 * p2) * cl_pitch + o;
-        out_cl[r] = __float2bfloat16(y0);
-        out_cl[r + cl_pitch] = __float2bfloat16(y1);
+        // even channel: low half, odd channel: high half of the packed word
+        if ((o & 1) == 0) {
+          cl0[o >> 1] = __bfloat16_as_ushort(__float2bfloat16(y0));
+          cl1[o >> 1] = __bfloat16_as_ushort(__float2bfloat16(y1));
+        } else {
+          cl0[o >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(y0))) << 16;
+          cl1[o >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(y1))) << 16;
+        }
+      }
+    }
+    if (out_cl) {
+      static_assert(C % 4 == 0, "channels-last rows are written as 8-byte vectors");
+      __nv_bfloat16* r0 = out_cl + (b * S + 2 * p2) * cl_pitch;
+      __nv_bfloat16* r1 = r0 + cl_pitch;
+#pragma unroll
+      for (int w2 = 0; w2 < C / 4; ++w2) {
+        reinterpret_cast<uint2*>(r0)[w2] = make_uint2(cl0[2 * w2], cl0[2 * w2 + 1]);
+        reinterpret_cast<uint2*>(r1)[w2] = make_uint2(cl1[2 * w2], cl1[2 * w2 + 1]);
       }
     }
   }

@@ -219,11 +219,21 @@ __device__ __forceinline__ void fence_acq_rel_sys() {
 // surrounding arithmetic and far below bf16 resolution): one MUFU.RCP, one MUFU.EX2 and a
 // degree-5 Horner polynomial.  cdf and pdf share the same exponential exp(-x^2/2), so
 // value + derivative cost ~16 instructions instead of two libm calls.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 struct GeluParts { float cdf; float pdf; };
 __device__ __forceinline__ GeluParts gelu_parts(float x) {
   const float u = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
-  const float e = exp2f(-1.44269504088896341f * u * u);               // exp(-x^2 / 2)
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  const float e = ex2_approx(-1.44269504088896341f * u * u);           // exp(-x^2 / 2)
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
