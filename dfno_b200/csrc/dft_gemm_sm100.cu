@@ -372,7 +372,7 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   uint32_t stage_total = 0;
   if (p.epi.mode == EPI_ROWMAJOR && p.epi.vec_ok && p.N % 8 == 0 && (p.N == 8 || p.N == 16 || p.N == 32 ||
       p.N == 64 || p.N == 128 || p.N == 256)) {
-    const uint32_t pitch = p.N * 4 + 16;
+    const uint32_t pitch = ((p.N + 15) / 16 * 16) * 4 + 16;   // whole 16-column chunks are staged
     const uint32_t need = 4 * 32 * pitch;
     if (L.b_bytes + 2 * L.a_tile_bytes + need <= budget) { L.stage_pitch = pitch; stage_total = need; }
   }

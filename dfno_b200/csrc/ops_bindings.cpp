@@ -119,6 +119,13 @@ void kreduce_gemm(const at::Tensor& A, int64_t lda, int64_t Ma, const at::Tensor
                            D.stride(0), sm_count(), cur_stream()), "kreduce_gemm");
 }
 
+std::vector<at::Tensor> gelu_probe(const at::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor y = at::empty_like(x), dy = at::empty_like(x);
+  check(dfno::gelu_probe(fptr(x), y.data_ptr<float>(), dy.data_ptr<float>(), x.numel(), cur_stream()), "gelu_probe");
+  return {y, dy};
+}
+
 void head_bwd(const at::Tensor& hcl, int64_t npos, int64_t C, int64_t CP, const at::Tensor& W3pad,
               const at::Tensor& W3Tpad, const at::Tensor& b3, const at::Tensor& W4, const at::Tensor& dout,
               const std::vector<int64_t>& radices, const std::vector<int64_t>& strides, at::Tensor& gcl,
@@ -148,4 +155,5 @@ void register_ops(pybind11::module& m) {
   m.def("p2p_allreduce_small", &p2p_allreduce_small);
   m.def("kreduce_gemm", &kreduce_gemm);
   m.def("head_bwd", &head_bwd);
+  m.def("gelu_probe", &gelu_probe);
 }

@@ -244,7 +244,7 @@ bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __res
     // channels-last rows (for the projection head) are assembled in registers and written as
     // 8-byte vectors: two rows of cl_pitch bf16 per thread
     uint32_t cl0[C / 2 + 1], cl1[C / 2 + 1];
-#pragma unroll
+#pragma unroll 4
     for (int o = 0; o < C; ++o) {
       const float2 s = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(spec_pre + base + o * S));
       float a0 = s.x, a1 = s.y;
@@ -327,6 +327,11 @@ bypass_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
   }
 }
 
+__global__ void gelu_probe_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ dy, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) { y[i] = gelu_erf(x[i]); dy[i] = gelu_erf_grad(x[i]); }
+}
+
 int grid_for(long long work_items, int threads, int num_sms, int per_sm) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms) * per_sm;
@@ -338,6 +343,12 @@ int grid_for(long long work_items, int threads, int num_sms, int per_sm) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+const char* gelu_probe(const float* x, float* y, float* dy, long long n, cudaStream_t s) {
+  gelu_probe_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, y, dy, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 const char* lift_fwd(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
                      const float* b2, void* h, LiftDims d, int num_sms, cudaStream_t s) {
   if (d.Z % 2) return "Z must be even";
