@@ -32,7 +32,7 @@ namespace dfno {
 
 static constexpr int kTileM = 128;
 static constexpr int kBlockK = 64;                 // bf16 elements per 128-byte swizzle row
-static constexpr int kNumThreads = 192;            // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+static constexpr int kMaxThreads = 64 + 128 * 4;   // warp0 TMA, warp1 MMA, then 4*E epilogue warps (E <= 4)
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kMaxStages = 4;
 
@@ -44,7 +44,7 @@ struct SmemLayout {
   uint32_t stage_pitch;   // bytes per staged row (fp32 row + 16 B pad)
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmParams p, const SmemLayout L) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -75,8 +75,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4);                 // one arrival per epilogue warp
-    mbar_init(&tempty[1], 4);
+    mbar_init(&tempty[0], (blockDim.x - 64) >> 5);   // one arrival per epilogue warp
+    mbar_init(&tempty[1], (blockDim.x - 64) >> 5);
     mbar_init(bfull, 1);
     fence_barrier_init();
   }
@@ -132,15 +132,22 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global / peer memory ==========
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    // E warps share each TMEM lane quarter (hardware: warp w may only touch lanes
+    // 32*(w%4)..+31) and split the accumulator's 16-column chunks round-robin.
+    const int E = (static_cast<int>(blockDim.x) - 64) >> 7;     // epilogue warps per lane quarter
+    const int q = warp & 3;                                      // TMEM lane quarter of this warp
+    const int e = (warp - 2) >> 2;                               // which slice of the columns
+    const int nthr_q = 32 * E;
     const int r_in_tile = q * 32 + lane;
     uint32_t acc = 0, acc_ph = 0;
     const int npairs = p.N >> 1;
+    float* s_part = reinterpret_cast<float*>(smem + L.stage_off);   // EPI_HEAD: [2][E][128] partial sums
     {
-      // per-CTA lookup tables (epilogue warps only; named barrier 1, 128 threads)
+      // per-CTA lookup tables (all epilogue warps; named barrier 1)
       const int et = threadIdx.x - 64;
+      const int nthr = 128 * E;
       if (p.epi.mode == EPI_PAIR_SCATTER) {
-        for (int j = et; j < npairs && j < 128; j += 128) {
+        for (int j = et; j < npairs && j < 128; j += nthr) {
           int jj = j, peer = 0;
           if (p.epi.peer_sel == PEER_BY_COL) { peer = jj / p.epi.peer_div; jj -= peer * p.epi.peer_div; }
           const int j0 = jj % p.epi.J[0], j1 = jj / p.epi.J[0];
@@ -148,10 +155,10 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           s_colpeer[j] = static_cast<uint8_t>(peer);
         }
       } else if (p.epi.mode == EPI_HEAD) {
-        for (int j = et; j < p.N; j += 128) { s_vec[j] = p.epi.v0[j]; s_vec[256 + j] = p.epi.v1[j]; }
+        for (int j = et; j < p.N; j += nthr) { s_vec[j] = p.epi.v0[j]; s_vec[256 + j] = p.epi.v1[j]; }
         if (et == 0) s_vec[511] = p.epi.v1[p.N];          // output bias stored right after the weights
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long row = static_cast<long long>(tile) * kTileM + r_in_tile;
@@ -160,12 +167,12 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_pad;
 
-      if (p.epi.mode == EPI_ROWMAJOR && L.stage_off != 0) {
-        // ---- coalesced row-major store: TMEM -> fp32 staging rows in smem (one 32-row slab
-        // per warp) -> each half-warp / quarter-warp writes whole rows contiguously
+      if (p.epi.mode == EPI_ROWMAJOR && L.stage_pitch != 0) {
+        // ---- coalesced row-major store: TMEM -> fp32 staging rows in smem (one 32-row slab per
+        // lane quarter) -> groups of lanes write whole rows contiguously
         uint8_t* slab = smem + L.stage_off + q * 32 * L.stage_pitch;
         float* myrow = reinterpret_cast<float*>(slab + lane * L.stage_pitch);
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
+        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -173,42 +180,55 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 4; ++i)
             reinterpret_cast<uint4*>(myrow + c0)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
-        __syncwarp();
+        tcgen05_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(nthr_q) : "memory");      // slab complete
         const int vec_per_row = p.N >> 3;                       // 8 outputs (16 B of bf16) per lane
         const int rows_per_it = 32 / vec_per_row;               // N = 128 -> 16 lanes per row, 2 rows / instr
         const int lr = lane / vec_per_row, lc = lane % vec_per_row;
         const long long row0 = static_cast<long long>(tile) * kTileM + q * 32;
+        const int step = rows_per_it * E;
         if (lr < rows_per_it) {
-          for (int rr = lr; rr < 32; rr += rows_per_it) {
-            const long long grow = row0 + rr;
-            if (grow >= p.M) break;
-            const float* srow = reinterpret_cast<const float*>(slab + rr * L.stage_pitch) + lc * 8;
-            float4 f0 = reinterpret_cast<const float4*>(srow)[0];
-            float4 f1 = reinterpret_cast<const float4*>(srow)[1];
-            if (p.epi.add_src != nullptr) {
-              const uint4 a = *reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) + grow * p.epi.ld_add + lc * 8);
-              float2 t;
-              t = unpack_bf16x2(a.x); f0.x += t.x; f0.y += t.y;
-              t = unpack_bf16x2(a.y); f0.z += t.x; f0.w += t.y;
-              t = unpack_bf16x2(a.z); f1.x += t.x; f1.y += t.y;
-              t = unpack_bf16x2(a.w); f1.z += t.x; f1.w += t.y;
+          for (int rb = lr + rows_per_it * e; rb < 32; rb += 4 * step) {
+            uint4 addv[4];
+            bool okv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                        // issue all global loads first
+              const int rr = rb + u * step;
+              okv[u] = rr < 32 && row0 + rr < p.M;
+              addv[u] = make_uint4(0, 0, 0, 0);
+              if (okv[u] && p.epi.add_src != nullptr)
+                addv[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) +
+                                                          (row0 + rr) * p.epi.ld_add + lc * 8);
             }
-            if (p.epi.out_fp32) {
-              float* o = reinterpret_cast<float*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8;
-              reinterpret_cast<float4*>(o)[0] = f0;
-              reinterpret_cast<float4*>(o)[1] = f1;
-            } else {
-              uint4 u;
-              u.x = pack_bf16x2(f0.x, f0.y); u.y = pack_bf16x2(f0.z, f0.w);
-              u.z = pack_bf16x2(f1.x, f1.y); u.w = pack_bf16x2(f1.z, f1.w);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (!okv[u]) continue;
+              const int rr = rb + u * step;
+              const long long grow = row0 + rr;
+              const float* srow = reinterpret_cast<const float*>(slab + rr * L.stage_pitch) + lc * 8;
+              float4 f0 = reinterpret_cast<const float4*>(srow)[0];
+              float4 f1 = reinterpret_cast<const float4*>(srow)[1];
+              float2 t;
+              t = unpack_bf16x2(addv[u].x); f0.x += t.x; f0.y += t.y;
+              t = unpack_bf16x2(addv[u].y); f0.z += t.x; f0.w += t.y;
+              t = unpack_bf16x2(addv[u].z); f1.x += t.x; f1.y += t.y;
+              t = unpack_bf16x2(addv[u].w); f1.z += t.x; f1.w += t.y;
+              if (p.epi.out_fp32) {
+                float* o = reinterpret_cast<float*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8;
+                reinterpret_cast<float4*>(o)[0] = f0;
+                reinterpret_cast<float4*>(o)[1] = f1;
+              } else {
+                uint4 u4;
+                u4.x = pack_bf16x2(f0.x, f0.y); u4.y = pack_bf16x2(f0.z, f0.w);
+                u4.z = pack_bf16x2(f1.x, f1.y); u4.w = pack_bf16x2(f1.z, f1.w);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = u4;
+              }
             }
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, %1;" ::"r"(6 + q), "r"(nthr_q) : "memory");      // slab drained
       } else if (p.epi.mode == EPI_ROWMAJOR) {
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
+        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -216,36 +236,24 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          const int ncol = p.epi.vec_ok ? min(16, p.N - c0) : -min(16, p.N - c0);
+          const int ncol = min(16, p.N - c0);
+          const bool vec = p.epi.vec_ok && ncol == 16;
           if (p.epi.add_src != nullptr) {
-            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) +
-                                     row * p.epi.ld_add + c0;
-            if (ncol == 16) {
-              const uint4 u0 = *reinterpret_cast<const uint4*>(a);
-              const uint4 u1 = *reinterpret_cast<const uint4*>(a + 8);
-              const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 t = unpack_bf16x2(w[i]);
-                f[2 * i] += t.x;
-                f[2 * i + 1] += t.y;
-              }
-            } else {
-              for (int i = 0; i < abs(ncol); ++i) f[i] += __bfloat162float(a[i]);
-            }
+            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) + row * p.epi.ld_add + c0;
+            for (int i = 0; i < ncol; ++i) f[i] += __bfloat162float(a[i]);
           }
           if (p.epi.out_fp32) {
             float* o = reinterpret_cast<float*>(p.epi.peers[0]) + row * p.epi.ldc + c0;
-            if (ncol == 16) {
+            if (vec) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             } else {
-              for (int i = 0; i < abs(ncol); ++i) o[i] = f[i];
+              for (int i = 0; i < ncol; ++i) o[i] = f[i];
             }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + row * p.epi.ldc + c0;
-            if (ncol == 16) {
+            if (vec) {
               uint4 u0, u1;
               u0.x = pack_bf16x2(f[0], f[1]);   u0.y = pack_bf16x2(f[2], f[3]);
               u0.z = pack_bf16x2(f[4], f[5]);   u0.w = pack_bf16x2(f[6], f[7]);
@@ -254,7 +262,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               reinterpret_cast<uint4*>(o)[0] = u0;
               reinterpret_cast<uint4*>(o)[1] = u1;
             } else {
-              for (int i = 0; i < abs(ncol); ++i) o[i] = __float2bfloat16(f[i]);
+              for (int i = 0; i < ncol; ++i) o[i] = __float2bfloat16(f[i]);
             }
           }
         }
@@ -279,7 +287,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         __nv_bfloat16* const rbase = reinterpret_cast<__nv_bfloat16*>(p.epi.peers[rpeer]) + roff;
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
+        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -297,10 +305,29 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else {
-        // ---- projection head: out = s0 + sum_j v1[j] * gelu(acc[j] + v0[j])
-        long long roff = p.epi.base_off;
-        {
-          uint32_t r = static_cast<uint32_t>(row_ok ? row : 0);
+        // ---- projection head: out = b4 + sum_j W4[j] * gelu(acc[j] + b3[j]); the E warps of a
+        // lane quarter each sum their column slice, warp e = 0 adds the partials and stores
+        float part = 0.f;
+        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (c0 + i < p.N) {
+              const float pre = __uint_as_float(v[i]) + s_vec[c0 + i];
+              part = fmaf(s_vec[256 + c0 + i], gelu_erf(pre), part);
+            }
+          }
+        }
+        float* mine = s_part + (acc * E + e) * 128 + r_in_tile;
+        if (e != 0) *mine = part;
+        tcgen05_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(nthr_q) : "memory");
+        if (e == 0 && row_ok) {
+          for (int k = 1; k < E; ++k) part += s_part[(acc * E + k) * 128 + r_in_tile];
+          long long roff = p.epi.base_off;
+          uint32_t r = static_cast<uint32_t>(row);
 #pragma unroll
           for (int l = 0; l < 4; ++l) {
             if (l < p.epi.nrl) {
@@ -310,21 +337,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               roff += static_cast<long long>(d) * p.epi.SR[l];
             }
           }
+          reinterpret_cast<float*>(p.epi.peers[0])[roff] = part + s_vec[511];
         }
-        float acc_out = s_vec[511];
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (c0 + i < p.N) {
-              const float pre = __uint_as_float(v[i]) + s_vec[c0 + i];
-              acc_out = fmaf(s_vec[256 + c0 + i], gelu_erf(pre), acc_out);
-            }
-          }
-        }
-        if (row_ok) reinterpret_cast<float*>(p.epi.peers[0])[roff] = acc_out;
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tcgen05_fence_before();
@@ -376,6 +390,8 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
     const uint32_t need = 4 * 32 * pitch;
     if (L.b_bytes + 2 * L.a_tile_bytes + need <= budget) { L.stage_pitch = pitch; stage_total = need; }
   }
+  const int E = p.epi.mode == EPI_HEAD ? 4 : (p.N > 16 ? 2 : 1);
+  if (p.epi.mode == EPI_HEAD) stage_total = 2 * 4 * 128 * 4;            // [2][E][128] partial sums
   L.stages = (budget - L.b_bytes - stage_total) / L.a_tile_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
   if (stage_total) L.stage_off = L.b_bytes + L.stages * L.a_tile_bytes + 4096;
@@ -399,7 +415,7 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   }
   const int num_tiles = static_cast<int>((p.M + kTileM - 1) / kTileM);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  dft_gemm_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, p, L);
+  dft_gemm_kernel<<<grid, 64 + 128 * E, smem_bytes, stream>>>(tmA, tmB, p, L);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

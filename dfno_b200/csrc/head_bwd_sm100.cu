@@ -21,7 +21,8 @@ namespace dfno {
 namespace {
 
 constexpr int kStagesH = 3;
-constexpr int kThreadsH = 192;
+constexpr int kEpiH = 4;                 // epilogue warps per TMEM lane quarter (one 32-column slice each)
+constexpr int kThreadsH = 64 + 128 * kEpiH;
 constexpr int kHid = 128;
 constexpr uint32_t kColsH = 512;
 // TMEM columns
@@ -85,8 +86,8 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < kStagesH; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(w_full, 1);
     mbar_init(&d1_full[0], 1); mbar_init(&d1_full[1], 1);
-    mbar_init(&d1_empty[0], 4); mbar_init(&d1_empty[1], 4);
-    mbar_init(p_full, 4);
+    mbar_init(&d1_empty[0], 4 * kEpiH); mbar_init(&d1_empty[1], 4 * kEpiH);
+    mbar_init(p_full, 4 * kEpiH);
     mbar_init(d2_full, 1);
     fence_barrier_init();
   }
@@ -170,6 +171,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue warps (thread = field position = TMEM lane) ==========
     const int q = warp & 3;
+    const int e = (warp - 2) >> 2;               // this warp's 32-column slice of the hidden layer
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     float acc_gb4 = 0.f;
@@ -192,13 +194,13 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         dout = p.dout[roff];
       }
-      acc_gb4 += dout;
+      if (e == 0) acc_gb4 += dout;
       mbar_wait(&d1_full[buf], (n >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t t1 = tmem_base + lane_addr + kD1 + buf * 128;
       uint8_t* prow = smem_p + r_in_tile * 128;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kHid; c0 += 32) {
+      {
+        const int c0 = 32 * e;
         float gsum[32], wsum[32];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -242,10 +244,10 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&d1_empty[buf]); mbar_arrive(p_full); }
-      // ---- dh tile
+      // ---- dh tile (every warp waits: P may not be overwritten before MMA2/MMA3 retired)
       mbar_wait(d2_full, n & 1);
       tcgen05_fence_after();
-      {
+      if (e == 0) {
         uint32_t v[16], w[16];
         tmem_ld_32x32b_x16(tmem_base + lane_addr + kD2, v);
         tmem_ld_32x32b_x16(tmem_base + lane_addr + kD2 + 16, w);
@@ -273,9 +275,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 4);
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 2);
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 1);
-    if (lane == 0) atomicAdd(s_gb4, acc_gb4);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (n > 0) {
+    if (lane == 0 && e == 0) atomicAdd(s_gb4, acc_gb4);
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiH) : "memory");
+    if (n > 0 && e == 0) {
       // all MMA3 of this CTA have completed: the last d2_full wait above covers them
       tcgen05_fence_after();
       uint32_t v[16], w[16];
