@@ -30,6 +30,10 @@ struct EpiParams {
   int nrl;
   int R[4];
   long long SR[4];
+  unsigned long long Rm[4];   // filled by the launcher: magic multipliers / shifts for fast division
+  int Rs[4];
+  unsigned long long Pm;
+  int Ps;
   int J[2];
   long long SJ[2];
   int peer_sel;

@@ -32,17 +32,48 @@ namespace dfno {
 
 static constexpr int kTileM = 128;
 static constexpr int kBlockK = 64;                 // bf16 elements per 128-byte swizzle row
-static constexpr int kMaxThreads = 64 + 128 * 4;   // warp0 TMA, warp1 MMA, then 4*E epilogue warps (E <= 4)
+static constexpr int kMaxThreads = 64 + 128 * 4;   // warp0 TMA, warp1 MMA, then E groups of 4 epilogue warps
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kMaxStages = 4;
+static constexpr int kMaxAcc = 8;                  // TMEM accumulator stages
 
 struct SmemLayout {
   uint32_t b_bytes;       // kblocks * n_pad * 128
   uint32_t a_tile_bytes;  // kblocks * 16384
   uint32_t stages;
-  uint32_t stage_off;     // byte offset of the epilogue staging area (0 = none)
-  uint32_t stage_pitch;   // bytes per staged row (fp32 row + 16 B pad)
+  uint32_t nacc;          // TMEM accumulator stages (multiple of the number of epilogue groups)
+  uint32_t stage_off;     // byte offset of the epilogue staging area
+  uint32_t stage_pitch;   // bytes per staged fp32 row (+16 B pad); 0 = direct stores
 };
+
+// floor(n / d) for n < 2^31 with a host-computed magic number
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, unsigned long long magic, int shift) {
+  return static_cast<uint32_t>((static_cast<unsigned long long>(n) * magic) >> shift);
+}
+
+// mixed-radix row address (shared by the scatter and head epilogues)
+__device__ __forceinline__ long long row_offset(const EpiParams& e, uint32_t r, int& peer) {
+  long long off = e.base_off;
+  peer = 0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (l < e.nrl) {
+      uint32_t d = r;
+      if (l != e.nrl - 1) {
+        const uint32_t q = fast_div(r, e.Rm[l], e.Rs[l]);
+        d = r - q * static_cast<uint32_t>(e.R[l]);
+        r = q;
+      }
+      if (e.peer_sel == PEER_BY_ROW && l == e.peer_lvl) {
+        const uint32_t pq = fast_div(d, e.Pm, e.Ps);
+        peer = static_cast<int>(pq);
+        d -= pq * static_cast<uint32_t>(e.peer_div);
+      }
+      off += static_cast<long long>(d) * e.SR[l];
+    }
+  }
+  return off;
+}
 
 __global__ void __launch_bounds__(kMaxThreads, 1)
 dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -51,13 +82,13 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + L.b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + L.stages * L.a_tile_bytes);
-  uint64_t* full = bars;                      // [stages]   TMA -> MMA
-  uint64_t* empty = bars + kMaxStages;        // [stages]   MMA -> TMA
-  uint64_t* tfull = bars + 2 * kMaxStages;    // [2]        MMA -> epilogue
-  uint64_t* tempty = tfull + 2;               // [2]        epilogue -> MMA
-  uint64_t* bfull = tempty + 2;               // [1]        B resident
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bfull + 1);
-  long long* s_coloff = reinterpret_cast<long long*>(bars + 16);        // [128] pair -> element offset
+  uint64_t* full = bars;                      // [4]   TMA -> MMA
+  uint64_t* empty = bars + 4;                 // [4]   MMA -> TMA
+  uint64_t* tfull = bars + 8;                 // [8]   MMA -> epilogue
+  uint64_t* tempty = bars + 16;               // [8]   epilogue -> MMA
+  uint64_t* bfull = bars + 24;                // [1]   B resident
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
+  long long* s_coloff = reinterpret_cast<long long*>(bars + 32);        // [128] pair -> element offset
   float* s_vec = reinterpret_cast<float*>(s_coloff + 128);              // [512] EPI_HEAD vectors
   uint8_t* s_colpeer = reinterpret_cast<uint8_t*>(s_vec + 512);         // [128] pair -> peer
 
@@ -65,6 +96,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int kblocks = p.k_pad / kBlockK;
   const int num_tiles = (p.M + kTileM - 1) / kTileM;
+  const int E = (static_cast<int>(blockDim.x) - 64) >> 7;      // epilogue groups (4 warps each)
+  const int nacc = static_cast<int>(L.nacc);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -73,10 +106,10 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(&tfull[0], 1);
-    mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], (blockDim.x - 64) >> 5);   // one arrival per epilogue warp
-    mbar_init(&tempty[1], (blockDim.x - 64) >> 5);
+    for (int a = 0; a < nacc; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);               // the four warps of the group that drains this stage
+    }
     mbar_init(bfull, 1);
     fence_barrier_init();
   }
@@ -107,15 +140,17 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad);
     const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
     mbar_wait(bfull, 0);
-    uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty[acc], acc_ph ^ 1);
+    uint32_t s = 0, ph = 0;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      const int a = n % nacc;
+      mbar_wait(&tempty[a], ((n / nacc) & 1) ^ 1);
       mbar_wait(&full[s], ph);
       tcgen05_fence_after();
       if (lane == 0) {
         const uint32_t a_base = smem_u32(smem_a + s * L.a_tile_bytes);
         const uint32_t b_base = smem_u32(smem_b);
-        const uint32_t d_tmem = tmem_base + acc * p.n_pad;
+        const uint32_t d_tmem = tmem_base + a * p.n_pad;
         for (int ks = 0; ks < ksteps; ++ks) {
           const int kb = ks >> 2, kk = ks & 3;
           const uint64_t adesc = umma_smem_desc_k128(a_base + kb * (kTileM * 128) + kk * 32);
@@ -123,25 +158,20 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(&empty[s]);               // smem stage may be refilled once the MMAs retire
-        umma_commit(&tfull[acc]);             // accumulator ready for the epilogue
+        umma_commit(&tfull[a]);               // accumulator ready for the epilogue
       }
       __syncwarp();
       if (++s == L.stages) { s = 0; ph ^= 1; }
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1;
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global / peer memory ==========
-    // E warps share each TMEM lane quarter (hardware: warp w may only touch lanes
-    // 32*(w%4)..+31) and split the accumulator's 16-column chunks round-robin.
-    const int E = (static_cast<int>(blockDim.x) - 64) >> 7;     // epilogue warps per lane quarter
+    // E groups of 4 warps (one per TMEM lane quarter; hardware: warp w may only touch lanes
+    // 32*(w%4)..+31).  Group g drains the tiles n = g, g+E, ... of this CTA, so E tile
+    // epilogues are in flight and their latency chains overlap.
     const int q = warp & 3;                                      // TMEM lane quarter of this warp
-    const int e = (warp - 2) >> 2;                               // which slice of the columns
-    const int nthr_q = 32 * E;
+    const int g = (warp - 2) >> 2;                               // epilogue group
     const int r_in_tile = q * 32 + lane;
-    uint32_t acc = 0, acc_ph = 0;
     const int npairs = p.N >> 1;
-    float* s_part = reinterpret_cast<float*>(smem + L.stage_off);   // EPI_HEAD: [2][E][128] partial sums
     {
       // per-CTA lookup tables (all epilogue warps; named barrier 1)
       const int et = threadIdx.x - 64;
@@ -160,19 +190,22 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int n = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      if (n % E != g) continue;
+      const int a = n % nacc;
       const long long row = static_cast<long long>(tile) * kTileM + r_in_tile;
       const bool row_ok = row < p.M;
-      mbar_wait(&tfull[acc], acc_ph);
+      mbar_wait(&tfull[a], (n / nacc) & 1);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.n_pad;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * p.n_pad;
 
       if (p.epi.mode == EPI_ROWMAJOR && L.stage_pitch != 0) {
-        // ---- coalesced row-major store: TMEM -> fp32 staging rows in smem (one 32-row slab per
-        // lane quarter) -> groups of lanes write whole rows contiguously
-        uint8_t* slab = smem + L.stage_off + q * 32 * L.stage_pitch;
+        // ---- coalesced row-major store: TMEM -> fp32 staging rows in smem (a private 32-row
+        // slab per warp) -> groups of lanes write whole rows contiguously
+        uint8_t* slab = smem + L.stage_off + ((g * 4 + q) * 32) * L.stage_pitch;
         float* myrow = reinterpret_cast<float*>(slab + lane * L.stage_pitch);
-        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -180,55 +213,55 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int i = 0; i < 4; ++i)
             reinterpret_cast<uint4*>(myrow + c0)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
+        // the accumulator is drained into smem: release the TMEM stage before the global stores
         tcgen05_fence_before();
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(nthr_q) : "memory");      // slab complete
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
         const int vec_per_row = p.N >> 3;                       // 8 outputs (16 B of bf16) per lane
         const int rows_per_it = 32 / vec_per_row;               // N = 128 -> 16 lanes per row, 2 rows / instr
         const int lr = lane / vec_per_row, lc = lane % vec_per_row;
         const long long row0 = static_cast<long long>(tile) * kTileM + q * 32;
-        const int step = rows_per_it * E;
-        if (lr < rows_per_it) {
-          for (int rb = lr + rows_per_it * e; rb < 32; rb += 4 * step) {
-            uint4 addv[4];
-            bool okv[4];
+        for (int rb = lr; rb < 32; rb += 4 * rows_per_it) {
+          uint4 addv[4];
+          bool okv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {                        // issue all global loads first
-              const int rr = rb + u * step;
-              okv[u] = rr < 32 && row0 + rr < p.M;
-              addv[u] = make_uint4(0, 0, 0, 0);
-              if (okv[u] && p.epi.add_src != nullptr)
-                addv[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) +
-                                                          (row0 + rr) * p.epi.ld_add + lc * 8);
-            }
+          for (int u = 0; u < 4; ++u) {                          // issue all global loads first
+            const int rr = rb + u * rows_per_it;
+            okv[u] = rr < 32 && row0 + rr < p.M;
+            addv[u] = make_uint4(0, 0, 0, 0);
+            if (okv[u] && p.epi.add_src != nullptr)
+              addv[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) +
+                                                        (row0 + rr) * p.epi.ld_add + lc * 8);
+          }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (!okv[u]) continue;
-              const int rr = rb + u * step;
-              const long long grow = row0 + rr;
-              const float* srow = reinterpret_cast<const float*>(slab + rr * L.stage_pitch) + lc * 8;
-              float4 f0 = reinterpret_cast<const float4*>(srow)[0];
-              float4 f1 = reinterpret_cast<const float4*>(srow)[1];
-              float2 t;
-              t = unpack_bf16x2(addv[u].x); f0.x += t.x; f0.y += t.y;
-              t = unpack_bf16x2(addv[u].y); f0.z += t.x; f0.w += t.y;
-              t = unpack_bf16x2(addv[u].z); f1.x += t.x; f1.y += t.y;
-              t = unpack_bf16x2(addv[u].w); f1.z += t.x; f1.w += t.y;
-              if (p.epi.out_fp32) {
-                float* o = reinterpret_cast<float*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8;
-                reinterpret_cast<float4*>(o)[0] = f0;
-                reinterpret_cast<float4*>(o)[1] = f1;
-              } else {
-                uint4 u4;
-                u4.x = pack_bf16x2(f0.x, f0.y); u4.y = pack_bf16x2(f0.z, f0.w);
-                u4.z = pack_bf16x2(f1.x, f1.y); u4.w = pack_bf16x2(f1.z, f1.w);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = u4;
-              }
+          for (int u = 0; u < 4; ++u) {
+            if (!okv[u]) continue;
+            const int rr = rb + u * rows_per_it;
+            const long long grow = row0 + rr;
+            const float* srow = reinterpret_cast<const float*>(slab + rr * L.stage_pitch) + lc * 8;
+            float4 f0 = reinterpret_cast<const float4*>(srow)[0];
+            float4 f1 = reinterpret_cast<const float4*>(srow)[1];
+            float2 t;
+            t = unpack_bf16x2(addv[u].x); f0.x += t.x; f0.y += t.y;
+            t = unpack_bf16x2(addv[u].y); f0.z += t.x; f0.w += t.y;
+            t = unpack_bf16x2(addv[u].z); f1.x += t.x; f1.y += t.y;
+            t = unpack_bf16x2(addv[u].w); f1.z += t.x; f1.w += t.y;
+            if (p.epi.out_fp32) {
+              float* o = reinterpret_cast<float*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8;
+              reinterpret_cast<float4*>(o)[0] = f0;
+              reinterpret_cast<float4*>(o)[1] = f1;
+            } else {
+              uint4 u4;
+              u4.x = pack_bf16x2(f0.x, f0.y); u4.y = pack_bf16x2(f0.z, f0.w);
+              u4.z = pack_bf16x2(f1.x, f1.y); u4.w = pack_bf16x2(f1.z, f1.w);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = u4;
             }
           }
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(6 + q), "r"(nthr_q) : "memory");      // slab drained
+        __syncwarp();                                            // slab reusable by this warp's next tile
+        continue;
       } else if (p.epi.mode == EPI_ROWMAJOR) {
-        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -239,8 +272,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int ncol = min(16, p.N - c0);
           const bool vec = p.epi.vec_ok && ncol == 16;
           if (p.epi.add_src != nullptr) {
-            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) + row * p.epi.ld_add + c0;
-            for (int i = 0; i < ncol; ++i) f[i] += __bfloat162float(a[i]);
+            const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.epi.add_src) + row * p.epi.ld_add + c0;
+            for (int i = 0; i < ncol; ++i) f[i] += __bfloat162float(ap[i]);
           }
           if (p.epi.out_fp32) {
             float* o = reinterpret_cast<float*>(p.epi.peers[0]) + row * p.epi.ldc + c0;
@@ -268,26 +301,10 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       } else if (p.epi.mode == EPI_PAIR_SCATTER) {
         // ---- pair scatter: (re, im) pairs to a mixed-radix address, possibly on a peer GPU
-        long long roff = p.epi.base_off;
-        int rpeer = 0;
-        {
-          uint32_t r = static_cast<uint32_t>(row_ok ? row : 0);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            if (l < p.epi.nrl) {
-              const uint32_t radix = static_cast<uint32_t>(p.epi.R[l]);
-              uint32_t d = r;
-              if (l != p.epi.nrl - 1) { const uint32_t qq = r / radix; d = r - qq * radix; r = qq; }
-              if (p.epi.peer_sel == PEER_BY_ROW && l == p.epi.peer_lvl) {
-                rpeer = d / p.epi.peer_div;
-                d -= rpeer * p.epi.peer_div;
-              }
-              roff += static_cast<long long>(d) * p.epi.SR[l];
-            }
-          }
-        }
+        int rpeer;
+        const long long roff = row_offset(p.epi, static_cast<uint32_t>(row_ok ? row : 0), rpeer);
         __nv_bfloat16* const rbase = reinterpret_cast<__nv_bfloat16*>(p.epi.peers[rpeer]) + roff;
-        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -305,10 +322,9 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else {
-        // ---- projection head: out = b4 + sum_j W4[j] * gelu(acc[j] + b3[j]); the E warps of a
-        // lane quarter each sum their column slice, warp e = 0 adds the partials and stores
-        float part = 0.f;
-        for (int c0 = 16 * e; c0 < p.N; c0 += 16 * E) {
+        // ---- projection head: out = b4 + sum_j W4[j] * gelu(acc[j] + b3[j])
+        float part = s_vec[511];
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
@@ -320,32 +336,15 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-        float* mine = s_part + (acc * E + e) * 128 + r_in_tile;
-        if (e != 0) *mine = part;
-        tcgen05_fence_before();
-        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "r"(nthr_q) : "memory");
-        if (e == 0 && row_ok) {
-          for (int k = 1; k < E; ++k) part += s_part[(acc * E + k) * 128 + r_in_tile];
-          long long roff = p.epi.base_off;
-          uint32_t r = static_cast<uint32_t>(row);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            if (l < p.epi.nrl) {
-              const uint32_t radix = static_cast<uint32_t>(p.epi.R[l]);
-              uint32_t d = r;
-              if (l != p.epi.nrl - 1) { const uint32_t qq = r / radix; d = r - qq * radix; r = qq; }
-              roff += static_cast<long long>(d) * p.epi.SR[l];
-            }
-          }
-          reinterpret_cast<float*>(p.epi.peers[0])[roff] = part + s_vec[511];
+        if (row_ok) {
+          int unused;
+          reinterpret_cast<float*>(p.epi.peers[0])[row_offset(p.epi, static_cast<uint32_t>(row), unused)] = part;
         }
       }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      // accumulator drained: hand the TMEM stage back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1;
+      if (lane == 0) mbar_arrive(&tempty[a]);
     }
     if (p.epi.peer_sel != PEER_NONE) __threadfence_system();   // publish peer stores
   }
@@ -358,6 +357,13 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
+static void magic_for(unsigned d, unsigned long long* magic, int* shift) {
+  int s = 0;
+  while ((1ull << s) < d) ++s;
+  *magic = ((1ull << (31 + s)) / d) + 1;
+  *shift = 31 + s;
+}
+
 const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, GemmParams p, int num_sms,
                             cudaStream_t stream) {
   if (p.M <= 0) return nullptr;
@@ -387,11 +393,22 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   if (p.epi.mode == EPI_ROWMAJOR && p.epi.vec_ok && p.N % 8 == 0 && (p.N == 8 || p.N == 16 || p.N == 32 ||
       p.N == 64 || p.N == 128 || p.N == 256)) {
     const uint32_t pitch = ((p.N + 15) / 16 * 16) * 4 + 16;   // whole 16-column chunks are staged
-    const uint32_t need = 4 * 32 * pitch;
-    if (L.b_bytes + 2 * L.a_tile_bytes + need <= budget) { L.stage_pitch = pitch; stage_total = need; }
+    L.stage_pitch = pitch;
   }
-  const int E = p.epi.mode == EPI_HEAD ? 4 : (p.N > 16 ? 2 : 1);
-  if (p.epi.mode == EPI_HEAD) stage_total = 2 * 4 * 128 * 4;            // [2][E][128] partial sums
+  // epilogue groups and TMEM accumulator stages
+  int E = 4;
+  if (512 / p.n_pad < E) E = 512 / p.n_pad;                              // n_pad 256 -> 2 groups
+  if (L.stage_pitch) {                                                   // one private slab per epilogue warp
+    while (E > 1 && L.b_bytes + 2 * L.a_tile_bytes + 4u * E * 32 * L.stage_pitch > budget) E >>= 1;
+    if (L.b_bytes + 2 * L.a_tile_bytes + 4u * E * 32 * L.stage_pitch > budget) { L.stage_pitch = 0; stage_total = 0; }
+    else stage_total = 4u * E * 32 * L.stage_pitch;
+  }
+  int nacc = 512 / p.n_pad;
+  if (nacc > kMaxAcc) nacc = kMaxAcc;
+  nacc = nacc / E * E;
+  L.nacc = static_cast<uint32_t>(nacc);
+  for (int l = 0; l < 4; ++l) magic_for(static_cast<unsigned>(p.epi.R[l] > 0 ? p.epi.R[l] : 1), &p.epi.Rm[l], &p.epi.Rs[l]);
+  magic_for(static_cast<unsigned>(p.epi.peer_div > 0 ? p.epi.peer_div : 1), &p.epi.Pm, &p.epi.Ps);
   L.stages = (budget - L.b_bytes - stage_total) / L.a_tile_bytes;
   if (L.stages > kMaxStages) L.stages = kMaxStages;
   if (stage_total) L.stage_off = L.b_bytes + L.stages * L.a_tile_bytes + 4096;

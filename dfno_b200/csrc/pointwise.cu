@@ -221,8 +221,8 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
 // ------------------------------------------------------------------------------------------
 // Each thread owns 2 consecutive z of one (b, x, y, t) and all C channels.
 // spec_pre: in = spectral branch, out (in place) = pre-activation (kept for the backward).
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, bool kCL>
+__global__ void __launch_bounds__(128)
 bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ spec_pre,
                        const float* __restrict__ W, __nv_bfloat16* __restrict__ out,
                        __nv_bfloat16* __restrict__ out_cl, int cl_pitch, int B, long long S, int save_pre) {
@@ -243,10 +243,15 @@ bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __res
     }
     // channels-last rows (for the projection head) are assembled in registers and written as
     // 8-byte vectors: two rows of cl_pitch bf16 per thread
-    uint32_t cl0[C / 2 + 1], cl1[C / 2 + 1];
-#pragma unroll 4
+    uint32_t cl0[kCL ? C / 2 + 1 : 1], cl1[kCL ? C / 2 + 1 : 1];
+    // all spectral-branch values are fetched up front: with few resident warps the loads
+    // must overlap each other, not the dependent FMA chains
+    uint32_t sp[C];
+#pragma unroll
+    for (int o = 0; o < C; ++o) sp[o] = *reinterpret_cast<const uint32_t*>(spec_pre + base + o * S);
+#pragma unroll
     for (int o = 0; o < C; ++o) {
-      const float2 s = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(spec_pre + base + o * S));
+      const float2 s = unpack_bf16x2(sp[o]);
       float a0 = s.x, a1 = s.y;
 #pragma unroll
       for (int i = 0; i < C; ++i) {
@@ -257,7 +262,7 @@ bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __res
       if (save_pre) *reinterpret_cast<uint32_t*>(spec_pre + base + o * S) = pack_bf16x2(a0, a1);
       const float y0 = gelu_erf(a0), y1 = gelu_erf(a1);
       if (out) *reinterpret_cast<uint32_t*>(out + base + o * S) = pack_bf16x2(y0, y1);
-      if (out_cl) {
+      if (kCL) {
         // even channel: low half, odd channel: high half of the packed word
         if ((o & 1) == 0) {
           cl0[o >> 1] = __bfloat16_as_ushort(__float2bfloat16(y0));
@@ -268,7 +273,7 @@ bypass_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __res
         }
       }
     }
-    if (out_cl) {
+    if (kCL) {
       static_assert(C % 4 == 0, "channels-last rows are written as 8-byte vectors");
       __nv_bfloat16* r0 = out_cl + (b * S + 2 * p2) * cl_pitch;
       __nv_bfloat16* r1 = r0 + cl_pitch;
@@ -419,11 +424,17 @@ const char* lift_bwd(const void* x, int x_is_bf16, const float* W1, const float*
 const char* bypass_gelu_fwd(const void* h, void* spec_pre, const float* W, void* out, void* out_cl, int cl_pitch,
                             int B, int C, long long S, int save_pre, int num_sms, cudaStream_t s) {
   if (S % 2) return "spatial size per channel must be even";
-  const int grid = grid_for(static_cast<long long>(B) * (S / 2), 256, num_sms, 4);
-  DFNO_DISPATCH_C(C, (bypass_gelu_fwd_kernel<kC><<<grid, 256, 0, s>>>(
-                         static_cast<const __nv_bfloat16*>(h), static_cast<__nv_bfloat16*>(spec_pre), W,
-                         static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_cl), cl_pitch, B, S,
-                         save_pre)));
+  const int grid = grid_for(static_cast<long long>(B) * (S / 2), 128, num_sms, 16);
+  if (out_cl) {
+    DFNO_DISPATCH_C(C, (bypass_gelu_fwd_kernel<kC, true><<<grid, 128, 0, s>>>(
+                           static_cast<const __nv_bfloat16*>(h), static_cast<__nv_bfloat16*>(spec_pre), W,
+                           static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_cl), cl_pitch, B, S,
+                           save_pre)));
+  } else {
+    DFNO_DISPATCH_C(C, (bypass_gelu_fwd_kernel<kC, false><<<grid, 128, 0, s>>>(
+                           static_cast<const __nv_bfloat16*>(h), static_cast<__nv_bfloat16*>(spec_pre), W,
+                           static_cast<__nv_bfloat16*>(out), nullptr, cl_pitch, B, S, save_pre)));
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
