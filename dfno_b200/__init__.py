@@ -13,4 +13,5 @@ from .parallel import *           # noqa: F401,F403
 from .utils import *              # noqa: F401,F403
 from .models import *             # noqa: F401,F403
 from .trainer import Trainer      # noqa: E402,F401
+from .data import *               # noqa: E402,F401,F403
 from .models.fused import FusedDistributedFNO, FusedAdam   # noqa: E402,F401
