@@ -416,6 +416,10 @@ class Repartition(nn.Module):
                 self.dtype = x.dtype       # nothing to agree on
             else:
                 self._discover(x)          # collective over all members
+        if self.P_in.active and tuple(x.shape) != tuple(self.fwd_plan.in_shape):
+            raise ValueError(f"Repartition was planned for local shards of shape {self.fwd_plan.in_shape} "
+                             f"(global {self.fwd_plan.global_shape}) but got {tuple(x.shape)}; use one "
+                             f"Repartition module per tensor shape")
         if self.fwd_plan.identity:
             return x
         return _RepartitionFn.apply(x, self.fwd_plan, self.bwd_plan, self.group, self.dtype)
