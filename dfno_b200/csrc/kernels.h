@@ -44,6 +44,11 @@ const char* p2p_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, int ran
 const char* p2p_allreduce_small(float* const* peer_bufs, float* out, long long n, int rank, int world,
                                 cudaStream_t s);
 
+// push all-to-all-v over peer memory: segment i of `send` ([send_off[i], send_off[i+1]) bytes) is stored at
+// byte offset dst_off[i] of peer i's receive buffer.  Follow with p2p_barrier before reading.
+const char* p2p_alltoall(const void* send, const long long* send_off, void* const* peer_recv, const long long* dst_off,
+                         int world, int ctas_per_peer, cudaStream_t s);
+
 // K-reduction GEMM: D[i, j] (+)= sum_k A[i, k] * B[j, k]; A: [Ma<=128, K], B: [Nb<=256, K] bf16 K-major.
 const char* kreduce_gemm(const void* A, long long lda, int Ma, const void* Bm, long long ldb, int Nb, long long K,
                          float* D, long long ldd, int num_sms, cudaStream_t s);

@@ -110,6 +110,20 @@ void p2p_allreduce_small(const std::vector<int64_t>& buf_ptrs, at::Tensor& out, 
         "p2p_allreduce_small");
 }
 
+void p2p_alltoall(const at::Tensor& send, const std::vector<int64_t>& send_off, const std::vector<int64_t>& recv_ptrs,
+                  const std::vector<int64_t>& dst_off, int64_t ctas_per_peer) {
+  const int world = static_cast<int>(recv_ptrs.size());
+  TORCH_CHECK(send.is_cuda() && send.is_contiguous(), "send must be a contiguous CUDA tensor");
+  TORCH_CHECK(static_cast<int>(send_off.size()) == world + 1 && static_cast<int>(dst_off.size()) == world,
+              "offset tables do not match the world size");
+  c10::cuda::CUDAGuard guard(send.device());
+  void* peers[8]; long long so[9]; long long doff[8];
+  for (int i = 0; i < 8; ++i) { peers[i] = reinterpret_cast<void*>(recv_ptrs[i < world ? i : 0]); doff[i] = i < world ? dst_off[i] : 0; }
+  for (int i = 0; i <= 8; ++i) so[i] = send_off[i <= world ? i : world];
+  check(dfno::p2p_alltoall(send.data_ptr(), so, peers, doff, world, static_cast<int>(ctas_per_peer), cur_stream()),
+        "p2p_alltoall");
+}
+
 // D[Ma, Nb] (fp32, pre-zeroed or accumulated) += A[Ma, K] * B[Nb, K]^T, K contiguous
 void kreduce_gemm(const at::Tensor& A, int64_t lda, int64_t Ma, const at::Tensor& Bm, int64_t ldb, int64_t Nb,
                   int64_t K, at::Tensor& D) {
@@ -153,6 +167,7 @@ void register_ops(pybind11::module& m) {
   m.def("adam_step", &adam_step);
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_allreduce_small", &p2p_allreduce_small);
+  m.def("p2p_alltoall", &p2p_alltoall);
   m.def("kreduce_gemm", &kreduce_gemm);
   m.def("head_bwd", &head_bwd);
   m.def("gelu_probe", &gelu_probe);

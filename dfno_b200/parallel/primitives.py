@@ -314,8 +314,37 @@ def build_repartition_plan(P_in: Partition, P_out: Partition, global_shape: Sequ
     return plan
 
 
-def _exchange(x: torch.Tensor, plan: RepartitionPlan, group, device, dtype) -> torch.Tensor:
-    """Pack -> all_to_all_single -> unpack for one direction of a plan."""
+_P2P_POOL = {}
+
+
+def _p2p_engine(group, ranks, needed_bytes: int):
+    """Shared peer-memory all-to-all engine for a rank set (grown collectively on demand:
+    ``needed_bytes`` is derived from the plans, hence identical on every rank)."""
+    import os
+    if os.environ.get("DFNO_P2P_REPARTITION", "1") == "0" or group is None or len(ranks) > 8:
+        return None
+    if dist.get_backend(group) != "nccl":
+        return None
+    key = tuple(ranks)
+    eng = _P2P_POOL.get(key)
+    if eng is None or eng.capacity < needed_bytes + 16 * len(ranks):
+        try:
+            from ..runtime.symm import P2PAllToAll
+            cap = 1 << max(20, int(needed_bytes + 16 * len(ranks) - 1).bit_length())
+            eng = P2PAllToAll(group, list(ranks).index(world_rank()), len(ranks), cap)
+        except Exception as e:                               # noqa: BLE001 - IPC unavailable: NCCL path
+            import warnings
+            warnings.warn(f"peer-memory Repartition unavailable ({e}); using NCCL all_to_all")
+            os.environ["DFNO_P2P_REPARTITION"] = "0"
+            return None
+        _P2P_POOL[key] = eng
+    return eng
+
+
+def _exchange(x: torch.Tensor, plan: RepartitionPlan, group, device, dtype, matrix=None) -> torch.Tensor:
+    """Pack -> all-to-all-v -> unpack for one direction of a plan.  On CUDA the exchange runs
+    over NVLink peer memory (``runtime.symm.P2PAllToAll``) when ``matrix`` (the full
+    receive-count table) is given; otherwise ``all_to_all_single`` (gloo / NCCL)."""
     is_c = dtype.is_complex
     width = 2 if is_c else 1
     rdtype = (torch.float32 if dtype == torch.complex64 else torch.float64) if is_c else dtype
@@ -328,8 +357,15 @@ def _exchange(x: torch.Tensor, plan: RepartitionPlan, group, device, dtype) -> t
             send[off:off + cnt * width].view(piece.shape).copy_(piece)
             off += cnt * width
     recv = torch.empty(sum(plan.recv_counts) * width, dtype=rdtype, device=device)
+    eng = None
+    if group is not None and matrix is not None and device.type == "cuda":
+        need = max(sum(-(-c * width * send.element_size() // 16) * 16 for c in row) for row in matrix)
+        eng = _p2p_engine(group, plan.ranks, need)
     if group is None:
         recv.copy_(send)
+    elif eng is not None:
+        recv = eng.exchange(send, [c * width for c in plan.send_counts],
+                            [[c * width for c in row] for row in matrix])
     else:
         dist.all_to_all_single(recv, send,
                                [c * width for c in plan.recv_counts],
@@ -350,15 +386,15 @@ def _exchange(x: torch.Tensor, plan: RepartitionPlan, group, device, dtype) -> t
 
 class _RepartitionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, fwd: RepartitionPlan, bwd: RepartitionPlan, group, dtype):
-        ctx.bwd, ctx.group, ctx.dtype = bwd, group, dtype
+    def forward(ctx, x, fwd: RepartitionPlan, bwd: RepartitionPlan, group, dtype, mats):
+        ctx.bwd, ctx.group, ctx.dtype, ctx.mats = bwd, group, dtype, mats
         ctx.in_shape = x.shape
-        return _exchange(x, fwd, group, x.device, dtype)
+        return _exchange(x, fwd, group, x.device, dtype, mats[0] if mats else None)
 
     @staticmethod
     def backward(ctx, g):
-        gx = _exchange(g, ctx.bwd, ctx.group, g.device, ctx.dtype)
-        return gx.reshape(ctx.in_shape) if gx.numel() == 0 else gx, None, None, None, None
+        gx = _exchange(g, ctx.bwd, ctx.group, g.device, ctx.dtype, ctx.mats[1] if ctx.mats else None)
+        return gx.reshape(ctx.in_shape) if gx.numel() == 0 else gx, None, None, None, None, None
 
 
 class Repartition(nn.Module):
@@ -383,6 +419,13 @@ class Repartition(nn.Module):
     def _build(self, global_shape) -> None:
         self.fwd_plan = build_repartition_plan(self.P_in, self.P_out, global_shape)
         self.bwd_plan = build_repartition_plan(self.P_out, self.P_in, global_shape)
+        # full receive-count tables (pure integer math) for the peer-memory data plane
+        self.mats = None
+        if self.group is not None and len(self.ranks) <= 8 and not self.fwd_plan.identity:
+            order = self.fwd_plan.ranks
+            f = [build_repartition_plan(self.P_in, self.P_out, global_shape, me=r).recv_counts for r in order]
+            b = [build_repartition_plan(self.P_out, self.P_in, global_shape, me=r).recv_counts for r in order]
+            self.mats = (f, b)
 
     def _discover(self, x: torch.Tensor) -> None:
         """Agree on global shape and dtype from the local shards (one object all-gather)."""
@@ -422,7 +465,7 @@ class Repartition(nn.Module):
                              f"Repartition module per tensor shape")
         if self.fwd_plan.identity:
             return x
-        return _RepartitionFn.apply(x, self.fwd_plan, self.bwd_plan, self.group, self.dtype)
+        return _RepartitionFn.apply(x, self.fwd_plan, self.bwd_plan, self.group, self.dtype, self.mats)
 
 
 #: DistDL's older name for the same operator (``experiment_navier_stokes.py:92,193``).

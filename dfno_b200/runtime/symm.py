@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 from ..ops import build
 
-__all__ = ["SymmetricBuffer", "PeerBarrier"]
+__all__ = ["SymmetricBuffer", "PeerBarrier", "P2PAllToAll"]
 
 
 class SymmetricBuffer:
@@ -76,3 +76,70 @@ class PeerBarrier:
             return
         self.epoch += 1
         self.pad._C.p2p_barrier(self.pad.peer_ptrs(), self.rank, self.epoch)
+
+
+class P2PAllToAll:
+    """All-to-all-v over peer memory (``csrc/p2p.cu: p2p_alltoall``): every rank stores its
+    per-peer segments straight into the peers' symmetric receive buffers over NVLink, then a
+    flag barrier publishes them.  Drop-in data plane for ``dist.all_to_all_single`` on one
+    NVSwitch box -- the NCCL-free Repartition (BASELINE config 5).
+
+    ``capacity_bytes`` is the largest receive total any rank will see; segments are padded to
+    16 bytes inside the buffers.
+    """
+
+    def __init__(self, group, rank: int, world: int, capacity_bytes: int, ctas_per_peer: int = 16):
+        self.group, self.rank, self.world = group, rank, world
+        self.capacity = int((capacity_bytes + 16 * world + 255) // 256 * 256)
+        self.recv = [SymmetricBuffer(self.capacity, group, rank, world) for _ in range(2)]   # double buffered
+        self.barrier = PeerBarrier(group, rank, world)
+        self.ctas = ctas_per_peer
+        self._flip = 0
+        self._C = build.load()
+
+    @staticmethod
+    def _pad16(n: int) -> int:
+        return (n + 15) // 16 * 16
+
+    def exchange(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts_matrix) -> torch.Tensor:
+        """``send``: flat contiguous tensor whose consecutive pieces of ``send_counts[p]``
+        elements go to peer ``p``.  ``recv_counts_matrix[d][s]``: elements rank ``s`` sends to
+        rank ``d`` (every rank can compute it from the Repartition plans).  Returns a flat
+        tensor with the pieces received from rank 0, 1, ... concatenated."""
+        es = send.element_size()
+        W = self.world
+        buf = self.recv[self._flip]
+        self._flip ^= 1
+        # byte layout of every destination's receive buffer: source segments padded to 16 B
+        dst_off = []
+        for d in range(W):
+            off = sum(self._pad16(recv_counts_matrix[d][s] * es) for s in range(self.rank))
+            dst_off.append(off)
+        # pack the send buffer with 16-byte aligned segments
+        so = [0]
+        for p in range(W):
+            so.append(so[-1] + self._pad16(int(send_counts[p]) * es))
+        if all(int(send_counts[p]) * es % 16 == 0 for p in range(W)):
+            packed = send.view(torch.uint8)
+        else:
+            packed = torch.zeros(so[-1], dtype=torch.uint8, device=send.device)
+            src = send.view(torch.uint8)
+            o = 0
+            for p in range(W):
+                nb = int(send_counts[p]) * es
+                packed[so[p]:so[p] + nb] = src[o:o + nb]
+                o += nb
+        self._C.p2p_alltoall(packed, so, buf.peer_ptrs(), dst_off, self.ctas)
+        self.barrier()
+        mine = recv_counts_matrix[self.rank]
+        total = sum(int(c) for c in mine)
+        out = torch.empty(total, dtype=send.dtype, device=send.device)
+        raw = buf.view([self.capacity], torch.uint8)
+        o_b, o_e = 0, 0
+        for s in range(W):
+            n = int(mine[s])
+            if n:
+                out[o_e:o_e + n] = raw[o_b:o_b + n * es].view(send.dtype)
+            o_b += self._pad16(n * es)
+            o_e += n
+        return out
