@@ -25,6 +25,14 @@ const char* bypass_gelu_fwd(const void* h, void* spec_pre, const float* W, void*
 const char* bypass_gelu_bwd(const void* dout, const void* dout_cl, int cl_pitch, const void* pre, const float* W,
                             void* dpre, void* dhb, int B, int C, long long S, int num_sms, cudaStream_t s);
 
+// tcgen05 versions (bypass_sm100.cu): TMA in/out, channel mixing on the tensor core, dW accumulated in TMEM.
+// Wpad / WTpad: bf16 [32, 64] zero-padded W[o, i] / W^T[i, o].  Need C <= 32 and S % 128 == 0.
+const char* bypass_fwd_tc(const void* h, void* spec_pre, const void* Wpad, void* out, void* out_cl, int cl_pitch,
+                          int B, int C, long long S, int save_pre, int num_sms, cudaStream_t stream);
+const char* bypass_bwd_tc(const void* dout, const void* dout_cl, int cl_pitch, void* pre_dpre, const void* h,
+                          const void* WTpad, void* dhb, float* dW, int B, int C, long long S, int num_sms,
+                          cudaStream_t stream);
+
 // spectral channel mixing over the local mode slab: x,y bf16 [B, C, Q, 2]; w fp32 [C, C, Q, 2]
 const char* spectral_mix_fwd(const void* x, const float* w, void* y, int B, int C, long long Q, cudaStream_t s);
 // dx = dy * conj(w) ; dw (+)= conj(x) * dy summed over the batch

@@ -17,12 +17,14 @@
 namespace dfno {
 
 namespace {
-constexpr int kStages = 4;
+constexpr int kStages = 8;
 constexpr int kThreads = 192;
 constexpr uint32_t kCols = 256;
 
 struct KrParams {
   int Ma, Nb, nb_pad;
+  int a_rows;              // rows of the A box (32 when Ma <= 32: the UMMA still reads 128 rows, the
+                           // extra accumulator lanes hold don't-care values that are never read)
   long long kblocks;       // total 64-wide K blocks
   float* D;
   long long ldd;
@@ -31,9 +33,9 @@ struct KrParams {
 __global__ void __launch_bounds__(kThreads, 1)
 kreduce_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KrParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t a_bytes = 128 * 128, b_bytes = p.nb_pad * 128;
+  const uint32_t a_bytes = p.a_rows * 128, b_bytes = p.nb_pad * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes + 16384);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* done = bars + 2 * kStages;
@@ -122,15 +124,18 @@ const char* kreduce_gemm(const void* A, long long lda, int Ma, const void* Bm, l
   if (K > (1ll << 31) - 64) return "kreduce: K too large for one launch";
   KrParams p;
   p.Ma = Ma; p.Nb = Nb; p.nb_pad = (Nb + 15) / 16 * 16;
+  p.a_rows = Ma <= 32 ? 32 : 128;
   p.kblocks = (K + 63) / 64;
   p.D = D; p.ldd = ldd;
   CUtensorMap tmA, tmB;
-  if (make_map_2d(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(Ma), static_cast<uint64_t>(lda), 64, 128))
+  if (make_map_2d(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(Ma), static_cast<uint64_t>(lda), 64,
+                  static_cast<uint32_t>(p.a_rows)))
     return "cuTensorMapEncodeTiled(A) failed";
   if (make_map_2d(&tmB, Bm, static_cast<uint64_t>(K), static_cast<uint64_t>(Nb), static_cast<uint64_t>(ldb), 64,
                   static_cast<uint32_t>(p.nb_pad)))
     return "cuTensorMapEncodeTiled(B) failed";
-  uint32_t smem_bytes = kStages * (128 * 128 + p.nb_pad * 128) + 256;
+  // + 16 KB slack: the M = 128 descriptor of the last stage reads past its 32-row box
+  uint32_t smem_bytes = kStages * (p.a_rows * 128 + p.nb_pad * 128) + 256 + 16384;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   static bool attr_set = false;
   if (!attr_set) {

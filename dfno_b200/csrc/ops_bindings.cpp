@@ -69,6 +69,26 @@ void bypass_gelu_bwd(const c10::optional<at::Tensor>& dout, const c10::optional<
                               static_cast<int>(B), static_cast<int>(C), S, sm_count(), cur_stream()), "bypass_gelu_bwd");
 }
 
+void bypass_fwd_tc(const at::Tensor& h, at::Tensor& spec_pre, const at::Tensor& Wpad, const c10::optional<at::Tensor>& out,
+                   const c10::optional<at::Tensor>& out_cl, int64_t cl_pitch, int64_t B, int64_t C, int64_t S, bool save_pre) {
+  TORCH_CHECK(Wpad.dim() == 2 && Wpad.size(0) == 32 && Wpad.size(1) == 64 && Wpad.is_contiguous(), "Wpad [32,64]");
+  c10::cuda::CUDAGuard guard(h.device());
+  check(dfno::bypass_fwd_tc(bptr(h), bptr(spec_pre), bptr(Wpad), out ? bptr(*out) : nullptr,
+                            out_cl ? bptr(*out_cl) : nullptr, static_cast<int>(cl_pitch), static_cast<int>(B),
+                            static_cast<int>(C), S, save_pre ? 1 : 0, sm_count(), cur_stream()), "bypass_fwd_tc");
+}
+
+void bypass_bwd_tc(const c10::optional<at::Tensor>& dout, const c10::optional<at::Tensor>& dout_cl, int64_t cl_pitch,
+                   at::Tensor& pre_dpre, const at::Tensor& h, const at::Tensor& WTpad, at::Tensor& dhb, at::Tensor& dW,
+                   int64_t B, int64_t C, int64_t S) {
+  TORCH_CHECK(dout.has_value() != dout_cl.has_value(), "give exactly one of dout / dout_cl");
+  TORCH_CHECK(WTpad.dim() == 2 && WTpad.size(0) == 32 && WTpad.size(1) == 64 && WTpad.is_contiguous(), "WTpad [32,64]");
+  c10::cuda::CUDAGuard guard(h.device());
+  check(dfno::bypass_bwd_tc(dout ? bptr(*dout) : nullptr, dout_cl ? bptr(*dout_cl) : nullptr,
+                            static_cast<int>(cl_pitch), bptr(pre_dpre), bptr(h), bptr(WTpad), bptr(dhb), fptr_mut(dW),
+                            static_cast<int>(B), static_cast<int>(C), S, sm_count(), cur_stream()), "bypass_bwd_tc");
+}
+
 void spectral_mix_fwd(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, int64_t B, int64_t C, int64_t Q) {
   c10::cuda::CUDAGuard guard(x.device());
   check(dfno::spectral_mix_fwd(bptr(x), fptr(w), bptr(y), static_cast<int>(B), static_cast<int>(C), Q, cur_stream()),
@@ -162,6 +182,8 @@ void register_ops(pybind11::module& m) {
   m.def("lift_bwd", &lift_bwd);
   m.def("bypass_gelu_fwd", &bypass_gelu_fwd);
   m.def("bypass_gelu_bwd", &bypass_gelu_bwd);
+  m.def("bypass_fwd_tc", &bypass_fwd_tc);
+  m.def("bypass_bwd_tc", &bypass_bwd_tc);
   m.def("spectral_mix_fwd", &spectral_mix_fwd);
   m.def("spectral_mix_bwd", &spectral_mix_bwd);
   m.def("adam_step", &adam_step);

@@ -163,6 +163,9 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
       }
       const __nv_bfloat16* src = dh + (((static_cast<long long>(b) * C * plane + xy) * d.T + t) * d.Z) + 2 * z2;
       const long long cstride = plane * d.T * d.Z;
+      uint32_t gv[C];                                     // all channel loads of this t in flight together
+#pragma unroll
+      for (int c = 0; c < C; ++c) gv[c] = ok ? *reinterpret_cast<const uint32_t*>(src + c * cstride) : 0u;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float v0 = sb2[c], v1 = sb2[c];
@@ -171,12 +174,9 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
           v0 = fmaf(sW2[c * CIN + ci], a1[0][ci], v0);
           v1 = fmaf(sW2[c * CIN + ci], a1[1][ci], v1);
         }
-        float g0 = 0.f, g1 = 0.f;
-        if (ok) {
-          const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + c * cstride));
-          g0 = g.x * gelu_erf_grad(v0);
-          g1 = g.y * gelu_erf_grad(v1);
-        }
+        const float2 g = unpack_bf16x2(gv[c]);
+        const float g0 = g.x * gelu_erf_grad(v0);
+        const float g1 = g.y * gelu_erf_grad(v1);
         accb2[c] += g0 + g1;
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {

@@ -344,6 +344,8 @@ class FusedDistributedFNO(nn.Module):
         self._saved: Dict[str, torch.Tensor] = {}
         self._train_bufs_ready = False
         self.chain_desc = pl.chain()
+        import os as _os
+        self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and _os.environ.get("DFNO_TC_BYPASS", "0") != "0")
 
     # ------------------------------------------------------------------ parameters
     def _seg(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -445,6 +447,12 @@ class FusedDistributedFNO(nn.Module):
         w3t[:pl.C] = W3.t().to(torch.bfloat16)
         return w3, w3t
 
+    def _wpad(self, W: torch.Tensor) -> torch.Tensor:
+        """[C, C] fp32 -> zero-padded bf16 [32, 64] tcgen05 operand (rows = output index)."""
+        out = torch.zeros(32, 64, device=self.device, dtype=torch.bfloat16)
+        out[:W.shape[0], :W.shape[1]] = W.to(torch.bfloat16)
+        return out
+
     def _w4b4(self) -> torch.Tensor:
         """``[W4 (H), b4 (1)]`` -- adjacent in the flat parameter buffer by construction."""
         off, _ = self.plan.segments["linear4.W"]
@@ -507,9 +515,13 @@ class FusedDistributedFNO(nn.Module):
         for k in range(self.num_blocks):
             last = k == self.num_blocks - 1
             self._spectral_chain(hs[k], pres[k], k, adj=False)
-            C_.bypass_gelu_fwd(hs[k], pres[k], self._seg(f"blocks.{k}.linear.W"),
-                               None if last else hs[k + 1], hcl if last else None, pl.CP,
-                               pl.B, pl.C, pl.S, save)
+            Wb = self._seg(f"blocks.{k}.linear.W")
+            if self.use_tc_bypass:
+                C_.bypass_fwd_tc(hs[k], pres[k], self._wpad(Wb), None if last else hs[k + 1],
+                                 hcl if last else None, pl.CP, pl.B, pl.C, pl.S, save)
+            else:
+                C_.bypass_gelu_fwd(hs[k], pres[k], Wb, None if last else hs[k + 1], hcl if last else None,
+                                   pl.CP, pl.B, pl.C, pl.S, save)
         return self._head_forward(hcl)
 
     def _backward(self, x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
@@ -529,13 +541,18 @@ class FusedDistributedFNO(nn.Module):
         for k in reversed(range(self.num_blocks)):
             last = k == self.num_blocks - 1
             Wb = self._seg(f"blocks.{k}.linear.W")
-            # dpre overwrites pre (same thread reads then writes each element)
-            C_.bypass_gelu_bwd(None if last else g, gcl if last else None, pl.CP, pres[k], Wb, pres[k], dhb,
-                               pl.B, pl.C, pl.S)
             gW = self._seg(f"blocks.{k}.linear.W", self.grad_flat)
-            for b in range(pl.B):
-                sl = slice(b * pl.C * pl.S, (b + 1) * pl.C * pl.S)
-                C_.kreduce_gemm(pres[k][sl], pl.S, pl.C, hs[k][sl], pl.S, pl.C, pl.S, gW)
+            if self.use_tc_bypass:
+                # one tcgen05 kernel: dpre (over pre), dhb = W^T dpre, dW accumulated in TMEM
+                C_.bypass_bwd_tc(None if last else g, gcl if last else None, pl.CP, pres[k], hs[k],
+                                 self._wpad(Wb.t()), dhb, gW, pl.B, pl.C, pl.S)
+            else:
+                # dpre overwrites pre (same thread reads then writes each element)
+                C_.bypass_gelu_bwd(None if last else g, gcl if last else None, pl.CP, pres[k], Wb, pres[k], dhb,
+                                   pl.B, pl.C, pl.S)
+                for b in range(pl.B):
+                    sl = slice(b * pl.C * pl.S, (b + 1) * pl.C * pl.S)
+                    C_.kreduce_gemm(pres[k][sl], pl.S, pl.C, hs[k][sl], pl.S, pl.C, pl.S, gW)
             self._spectral_chain(pres[k], g, k, adj=True, add=dhb)
         C_.lift_bwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
                     self._seg("linear2.b"), g, self._seg("linear1.W", self.grad_flat),
