@@ -46,8 +46,9 @@ const char* adam_step(float* p, const float* g, float* m, float* v, long long n,
 
 // cross-GPU flag barrier over NVLink-mapped signal pads: every rank bumps its slot on each
 // peer to `epoch`, then waits until all of its own slots reached `epoch`.
+// timeout_ns > 0 bounds the spin: a late peer makes the kernel record the slot and trap (failure detection).
 const char* p2p_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, int rank, int world, uint32_t epoch,
-                        cudaStream_t s);
+                        unsigned long long timeout_ns, cudaStream_t s);
 // sum-all-reduce of a small fp32 vector through peer reads (every rank reads all peers' copies)
 const char* p2p_allreduce_small(float* const* peer_bufs, float* out, long long n, int rank, int world,
                                 cudaStream_t s);

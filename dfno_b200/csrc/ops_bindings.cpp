@@ -114,12 +114,12 @@ void adam_step(at::Tensor& p, const at::Tensor& g, at::Tensor& m, at::Tensor& v,
                         static_cast<float>(grad_scale), sm_count(), cur_stream()), "adam_step");
 }
 
-void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t epoch) {
+void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t epoch, double timeout_s) {
   const int world = static_cast<int>(flag_ptrs.size());
   uint32_t* peers[8];
   for (int i = 0; i < 8; ++i) peers[i] = reinterpret_cast<uint32_t*>(flag_ptrs[i < world ? i : 0]);
   check(dfno::p2p_barrier(peers, peers[rank], static_cast<int>(rank), world, static_cast<uint32_t>(epoch),
-                          cur_stream()), "p2p_barrier");
+                          static_cast<unsigned long long>(timeout_s * 1e9), cur_stream()), "p2p_barrier");
 }
 
 void p2p_allreduce_small(const std::vector<int64_t>& buf_ptrs, at::Tensor& out, int64_t n, int64_t rank) {

@@ -25,13 +25,30 @@ namespace {
 struct PeerFlags { uint32_t* p[8]; };
 struct PeerBufs { const float* p[8]; };
 
-__global__ void p2p_barrier_kernel(PeerFlags peers, uint32_t* my_flags, int rank, int world, uint32_t epoch) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Failure detection: a peer that died (or never reached the barrier) would hang every other
+// GPU of the box forever -- the reference has exactly this failure mode with MPI (SURVEY.md
+// 5.3).  The spin is bounded: after `timeout_ns` the slot that is late is recorded in
+// my_flags[16 + r] and the kernel traps, so the hang surfaces as a CUDA error on this rank.
+__global__ void p2p_barrier_kernel(PeerFlags peers, uint32_t* my_flags, int rank, int world, uint32_t epoch,
+                                   unsigned long long timeout_ns) {
   const int r = threadIdx.x;
   if (r < world) {
     __threadfence_system();
     st_release_sys(peers.p[r] + rank, epoch);
+    const unsigned long long t0 = global_timer_ns();
     // epochs only grow; signed difference tolerates wrap-around
     while (static_cast<int32_t>(ld_acquire_sys(my_flags + r) - epoch) < 0) {
+      if (timeout_ns && global_timer_ns() - t0 > timeout_ns) {
+        my_flags[16 + r] = epoch;                 // which peer / which epoch never arrived
+        __threadfence_system();
+        asm volatile("trap;");
+      }
     }
   }
 }
@@ -100,11 +117,11 @@ const char* p2p_alltoall(const void* send, const long long* send_off, void* cons
 }
 
 const char* p2p_barrier(uint32_t* const* peer_flags, uint32_t* my_flags, int rank, int world, uint32_t epoch,
-                        cudaStream_t s) {
+                        unsigned long long timeout_ns, cudaStream_t s) {
   if (world < 1 || world > 8) return "p2p_barrier: world size must be 1..8";
   PeerFlags pf;
   for (int i = 0; i < 8; ++i) pf.p[i] = peer_flags[i < world ? i : 0];
-  p2p_barrier_kernel<<<1, 32, 0, s>>>(pf, my_flags, rank, world, epoch);
+  p2p_barrier_kernel<<<1, 32, 0, s>>>(pf, my_flags, rank, world, epoch, timeout_ns);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -66,16 +66,24 @@ class SymmetricBuffer:
 class PeerBarrier:
     """Device-side flag barrier across the ranks sharing a signal pad (``p2p.cu``)."""
 
-    def __init__(self, group=None, rank: int = 0, world: int = 1):
+    def __init__(self, group=None, rank: int = 0, world: int = 1, timeout_s: Optional[float] = None):
+        import os
         self.rank, self.world = rank, world
         self.epoch = 0
+        # bounded spin: a peer that never arrives turns into a CUDA error instead of a hang
+        self.timeout_s = float(os.environ.get("DFNO_BARRIER_TIMEOUT_S", "60")) if timeout_s is None else timeout_s
         self.pad = SymmetricBuffer(256, group, rank, world) if world > 1 else None
 
     def __call__(self) -> None:
         if self.world <= 1:
             return
         self.epoch += 1
-        self.pad._C.p2p_barrier(self.pad.peer_ptrs(), self.rank, self.epoch)
+        self.pad._C.p2p_barrier(self.pad.peer_ptrs(), self.rank, self.epoch, self.timeout_s)
+
+    def late_peers(self):
+        """After a barrier timeout: ``{peer: epoch}`` of the slots that never arrived."""
+        flags = self.pad.view([64], torch.int32).cpu().tolist()
+        return {r: flags[16 + r] for r in range(self.world) if flags[16 + r] != 0}
 
 
 class P2PAllToAll:
