@@ -113,6 +113,8 @@ def main():
         print(json.dumps({"impl": "reference", "unavailable": why}))
         return 0
 
+    if args.impl == "baseline":
+        os.environ["DFNO_P2P_REPARTITION"] = "0"       # stock NCCL all_to_all / broadcast / reduce only
     import torch
     import torch.distributed as dist
     import dfno_b200 as d
