@@ -163,6 +163,7 @@ bypass_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
       __nv_bfloat16* clrow = p.out_cl ? p.out_cl + (static_cast<long long>(b) * p.S + p0 + t) * p.cl_pitch : nullptr;
+      uint32_t pk[16];                                      // channels-last row, two channels per word
 #pragma unroll
       for (int o = 0; o < 32; ++o) {
         if (o < p.C) {
@@ -170,9 +171,21 @@ bypass_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_const
           const float pre = __uint_as_float(v[o]) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(st + off));
           *reinterpret_cast<__nv_bfloat16*>(st + off) = __float2bfloat16(pre);
           const __nv_bfloat16 y = __float2bfloat16(gelu_erf(pre));
-          if (clrow) clrow[o] = y;
-          else *reinterpret_cast<__nv_bfloat16*>(ht + off) = y;
+          if (clrow) {
+            const uint32_t bits = __bfloat16_as_ushort(y);
+            if (o & 1) pk[o >> 1] |= bits << 16; else pk[o >> 1] = bits;
+          } else {
+            *reinterpret_cast<__nv_bfloat16*>(ht + off) = y;
+          }
+        } else if ((o & 1) == 0) {
+          pk[o >> 1] = 0;
         }
+      }
+      if (clrow) {                                          // 16-byte vectors; the pitch is a multiple of 8 channels
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          if (8 * w < p.cl_pitch)
+            reinterpret_cast<uint4*>(clrow)[w] = make_uint4(pk[4 * w], pk[4 * w + 1], pk[4 * w + 2], pk[4 * w + 3]);
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
@@ -302,13 +315,22 @@ bypass_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
       uint8_t* pt = stage0 + s * 3 * kTile;
       uint8_t* gt = pt + kTile;
       mbar_wait(&full[s], (n / kStagesBw) & 1);
-      const __nv_bfloat16* clrow = cl_in ? p.dout_cl + (static_cast<long long>(b) * p.S + p0 + t) * p.cl_pitch : nullptr;
+      uint32_t pk[16];
+      if (cl_in) {                                          // this position's channels-last gradient row
+        const uint4* clrow = reinterpret_cast<const uint4*>(p.dout_cl + (static_cast<long long>(b) * p.S + p0 + t) * p.cl_pitch);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if (8 * w < p.cl_pitch) u = clrow[w];
+          pk[4 * w] = u.x; pk[4 * w + 1] = u.y; pk[4 * w + 2] = u.z; pk[4 * w + 3] = u.w;
+        }
+      }
 #pragma unroll
       for (int o = 0; o < 32; ++o) {
         if (o < p.C) {
           const uint32_t off = tile_off(o, t);
           const float pre = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(pt + off));
-          const float dy = cl_in ? __bfloat162float(clrow[o])
+          const float dy = cl_in ? __uint_as_float((o & 1) ? (pk[o >> 1] & 0xffff0000u) : (pk[o >> 1] << 16))
                                  : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(gt + off));
           *reinterpret_cast<__nv_bfloat16*>(pt + off) = __float2bfloat16(dy * gelu_erf_grad(pre));
         }

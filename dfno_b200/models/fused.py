@@ -345,7 +345,7 @@ class FusedDistributedFNO(nn.Module):
         self._train_bufs_ready = False
         self.chain_desc = pl.chain()
         import os as _os
-        self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and _os.environ.get("DFNO_TC_BYPASS", "0") != "0")
+        self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and _os.environ.get("DFNO_TC_BYPASS", "1") != "0")
 
     # ------------------------------------------------------------------ parameters
     def _seg(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
