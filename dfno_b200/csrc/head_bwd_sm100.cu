@@ -27,8 +27,8 @@ constexpr int kHid = 128;
 constexpr uint32_t kColsH = 512;
 // TMEM columns
 constexpr uint32_t kD1 = 0;      // 2 x 128 : pre-activations (double buffered)
-constexpr uint32_t kD2 = 256;    // 32      : dh tile
-constexpr uint32_t kD3 = 288;    // 32      : dW3 accumulator [hid lanes, c]
+constexpr uint32_t kD2 = 256;    // 2 x 32  : dh tiles (double buffered with P)
+constexpr uint32_t kD3 = 320;    // 32      : dW3 accumulator [hid lanes, c]
 
 struct HeadBwdParams {
   long long npos;
@@ -61,18 +61,19 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_w3 = smem;                          // [128 hid][64 c]   K-major (K = c)      16 KB
   uint8_t* smem_w3t = smem + 16384;                 // 2 x [32 c][64 hid] K-major (K = hid)    8 KB
-  uint8_t* smem_p = smem + 24576;                   // 2 x [128 pos][64 hid]                  32 KB
-  uint8_t* smem_a = smem + 57344;                   // stages x [128 pos][64 c]               48 KB
+  uint8_t* smem_p = smem + 24576;                   // 2 buffers x 2 x [128 pos][64 hid]      64 KB
+  uint8_t* smem_a = smem + 90112;                   // stages x [128 pos][64 c]               48 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kStagesH * 16384);
   uint64_t* a_full = bars;            // [3]
   uint64_t* a_empty = bars + 3;       // [3]
   uint64_t* w_full = bars + 6;
   uint64_t* d1_full = bars + 7;       // [2]
   uint64_t* d1_empty = bars + 9;      // [2]
-  uint64_t* p_full = bars + 11;
-  uint64_t* d2_full = bars + 12;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
-  float* s_b3 = reinterpret_cast<float*>(bars + 16);   // [128]
+  uint64_t* p_full = bars + 11;       // [2]
+  uint64_t* d2_full = bars + 13;      // [2]
+  uint64_t* all_done = bars + 15;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_b3 = reinterpret_cast<float*>(bars + 20);   // [128]
   float* s_w4 = s_b3 + 128;                            // [128]
   float* s_gb3 = s_w4 + 128;                           // [128] CTA partial sums
   float* s_gw4 = s_gb3 + 128;                          // [128]
@@ -87,8 +88,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_init(w_full, 1);
     mbar_init(&d1_full[0], 1); mbar_init(&d1_full[1], 1);
     mbar_init(&d1_empty[0], 4 * kEpiH); mbar_init(&d1_empty[1], 4 * kEpiH);
-    mbar_init(p_full, 4 * kEpiH);
-    mbar_init(d2_full, 1);
+    mbar_init(&p_full[0], 4 * kEpiH); mbar_init(&p_full[1], 4 * kEpiH);
+    mbar_init(&d2_full[0], 1); mbar_init(&d2_full[1], 1);
+    mbar_init(all_done, 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 128; i += kThreadsH) {
@@ -127,16 +129,17 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int n = 0;
     uint32_t prev_stage = 0;
     auto part2 = [&](int m, uint32_t stage) {
-      mbar_wait(p_full, m & 1);
+      const int pb = m & 1;                                   // P / D2 buffer of this tile
+      mbar_wait(&p_full[pb], (m >> 1) & 1);
       tcgen05_fence_after();
       if (lane == 0) {
-        const uint32_t pbase = smem_u32(smem_p);
+        const uint32_t pbase = smem_u32(smem_p + pb * 32768);
         const uint32_t abase = smem_u32(smem_a + stage * 16384);
         const uint32_t wtbase = smem_u32(smem_w3t);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {   // K = hid, 16 per instruction; 64-wide blocks of P / W3T
           const int kb = ks >> 2, kk = ks & 3;
-          umma_bf16_ss(tmem_base + kD2, umma_smem_desc_k128(pbase + kb * 16384 + kk * 32),
+          umma_bf16_ss(tmem_base + kD2 + pb * 32, umma_smem_desc_k128(pbase + kb * 16384 + kk * 32),
                        umma_smem_desc_k128(wtbase + kb * 4096 + kk * 32), idesc2, ks > 0 ? 1u : 0u);
         }
 #pragma unroll
@@ -144,7 +147,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           umma_bf16_ss(tmem_base + kD3, umma_smem_desc_mn128(pbase + ks * 2048, 16384, 1024),
                        umma_smem_desc_mn128(abase + ks * 2048, 16384, 1024), idesc3, (m > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(d2_full);
+        umma_commit(&d2_full[pb]);
         umma_commit(&a_empty[stage]);
       }
       __syncwarp();
@@ -168,6 +171,8 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (++s == kStagesH) { s = 0; ph ^= 1; }
     }
     if (n > 0) part2(n - 1, prev_stage);
+    if (lane == 0) umma_commit(all_done);
+    __syncwarp();
   } else {
     // ===================== epilogue warps (thread = field position = TMEM lane) ==========
     const int q = warp & 3;
@@ -198,7 +203,10 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&d1_full[buf], (n >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t t1 = tmem_base + lane_addr + kD1 + buf * 128;
-      uint8_t* prow = smem_p + r_in_tile * 128;
+      const int pb = n & 1;
+      // the buffer was last read by the MMAs of tile n-2: already retired unless we run far ahead
+      if (n >= 2) mbar_wait(&d2_full[pb], ((n >> 1) - 1) & 1);
+      uint8_t* prow = smem_p + pb * 32768 + r_in_tile * 128;
       {
         const int c0 = 32 * e;
         float gsum[32], wsum[32];
@@ -243,14 +251,14 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tcgen05_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&d1_empty[buf]); mbar_arrive(p_full); }
-      // ---- dh tile (every warp waits: P may not be overwritten before MMA2/MMA3 retired)
-      mbar_wait(d2_full, n & 1);
-      tcgen05_fence_after();
+      if (lane == 0) { mbar_arrive(&d1_empty[buf]); mbar_arrive(&p_full[pb]); }
+      // ---- dh tile: only the e == 0 warps read it back
       if (e == 0) {
+        mbar_wait(&d2_full[pb], (n >> 1) & 1);
+        tcgen05_fence_after();
         uint32_t v[16], w[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + kD2, v);
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + kD2 + 16, w);
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + kD2 + pb * 32, v);
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + kD2 + pb * 32 + 16, w);
         tmem_ld_wait();
         if (row_ok) {
           __nv_bfloat16* o = p.gcl + row * p.CP;
@@ -278,7 +286,7 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0 && e == 0) atomicAdd(s_gb4, acc_gb4);
     asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiH) : "memory");
     if (n > 0 && e == 0) {
-      // all MMA3 of this CTA have completed: the last d2_full wait above covers them
+      mbar_wait(all_done, 0);                    // every MMA of this CTA has retired
       tcgen05_fence_after();
       uint32_t v[16], w[16];
       tmem_ld_32x32b_x16(tmem_base + lane_addr + kD3, v);
@@ -314,7 +322,7 @@ const char* head_bwd(const void* hcl, long long npos, int C, int CP, const void*
     return "cuTensorMapEncodeTiled(h) failed";
   if (make_map_2d(&tmW3, W3pad, 64, 128, 64, 64, 128)) return "cuTensorMapEncodeTiled(W3) failed";
   if (make_map_2d(&tmW3T, W3Tpad, 128, 32, 128, 64, 32)) return "cuTensorMapEncodeTiled(W3T) failed";
-  const uint32_t smem_bytes = 57344 + kStagesH * 16384 + 4096;
+  const uint32_t smem_bytes = 90112 + kStagesH * 16384 + 4096;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
