@@ -248,10 +248,28 @@ class DistributedFNO(nn.Module):
         self.device, self.dtype = device, dtype
         if len(self.in_shape) != P_x.dim:
             raise ValueError(f"in_shape {self.in_shape} does not match partition rank {P_x.dim}")
+        # The lift / projection contract the time and channel axes locally.  The reference is
+        # silently wrong when those axes are partitioned; here such a P_x
+        # is *defined*: the field is re-sharded once onto a work partition whose time/channel
+        # workers are folded onto the roomiest spatial axis, the network runs there, and the
+        # output is re-sharded back (BASELINE.json config 4: 8-way time-axis partition).
+        self.P_outer = P_x
+        self.R_in = self.R_out = None
         if int(P_x.shape[-1]) != 1 or int(P_x.shape[1]) != 1:
-            raise NotImplementedError(
-                "the time and channel axes are contracted locally by the lift/projection; "
-                "partition the spatial (or batch) axes instead")
+            work = [int(v) for v in P_x.shape]
+            extra = work[1] * work[-1]
+            work[1] = work[-1] = 1
+            sp = list(range(2, P_x.dim - 1))
+            tgt = max(sp, key=lambda d: self.in_shape[d] / work[d])
+            work[tgt] *= extra
+            if work[tgt] > self.in_shape[tgt]:
+                raise ValueError(f"cannot fold {extra} time/channel workers onto a spatial axis of {self.in_shape}")
+            out_shape = [self.in_shape[0], 1, *self.in_shape[2:-1], self.out_timesteps]
+            P_work = P_x.create_cartesian_topology_partition(work)
+            self.R_in = Repartition(P_x, P_work, self.in_shape, dtype=dtype)
+            self.R_out = Repartition(P_work, P_x, out_shape, dtype=dtype)
+            P_x = P_work
+        self.P_work = P_x
 
         self.block_in_shape = [self.in_shape[0], self.width, *self.in_shape[2:-1], self.out_timesteps]
         kw = dict(device=device, dtype=dtype)
@@ -269,12 +287,16 @@ class DistributedFNO(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         dt = 0.0
+        if self.R_in is not None:
+            x = self.R_in(x)
         x = F.gelu(self.linear1(x)); dt += self.linear1.dt_comm
         x = F.gelu(self.linear2(x)); dt += self.linear2.dt_comm
         for blk in self.blocks:
             x = blk(x); dt += blk.dt_comm
         x = F.gelu(self.linear3(x)); dt += self.linear3.dt_comm
         x = self.linear4(x); dt += self.linear4.dt_comm
+        if self.R_out is not None:
+            x = self.R_out(x)
         self.dt_comm = dt
         return x
 

@@ -103,11 +103,32 @@ class P2PAllToAll:
         self.barrier = PeerBarrier(group, rank, world)
         self.ctas = ctas_per_peer
         self._flip = 0
+        self._cache = {}
         self._C = build.load()
 
     @staticmethod
     def _pad16(n: int) -> int:
         return (n + 15) // 16 * 16
+
+    def _layout(self, es: int, send_counts, recv_counts_matrix):
+        """Byte offsets for one (element size, counts) signature; cached -- the models reuse a
+        handful of signatures every step."""
+        key = (es, tuple(int(c) for c in send_counts), tuple(tuple(int(c) for c in r) for r in recv_counts_matrix))
+        hit = self._cache.get(key)
+        if hit is None:
+            W = self.world
+            dst_off = [sum(self._pad16(recv_counts_matrix[d][s] * es) for s in range(self.rank)) for d in range(W)]
+            so = [0]
+            for p in range(W):
+                so.append(so[-1] + self._pad16(int(send_counts[p]) * es))
+            aligned_send = all(int(send_counts[p]) * es % 16 == 0 for p in range(W))
+            mine = [int(c) for c in recv_counts_matrix[self.rank]]
+            aligned_recv = all(c * es % 16 == 0 for c in mine)
+            per_peer = max(so[p + 1] - so[p] for p in range(W))
+            ctas = max(1, min(32, per_peer // 65536))
+            hit = (dst_off, so, aligned_send, mine, aligned_recv, ctas)
+            self._cache[key] = hit
+        return hit
 
     def exchange(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts_matrix) -> torch.Tensor:
         """``send``: flat contiguous tensor whose consecutive pieces of ``send_counts[p]``
@@ -118,18 +139,10 @@ class P2PAllToAll:
         W = self.world
         buf = self.recv[self._flip]
         self._flip ^= 1
-        # byte layout of every destination's receive buffer: source segments padded to 16 B
-        dst_off = []
-        for d in range(W):
-            off = sum(self._pad16(recv_counts_matrix[d][s] * es) for s in range(self.rank))
-            dst_off.append(off)
-        # pack the send buffer with 16-byte aligned segments
-        so = [0]
-        for p in range(W):
-            so.append(so[-1] + self._pad16(int(send_counts[p]) * es))
-        if all(int(send_counts[p]) * es % 16 == 0 for p in range(W)):
+        dst_off, so, aligned_send, mine, aligned_recv, ctas = self._layout(es, send_counts, recv_counts_matrix)
+        if aligned_send:
             packed = send.view(torch.uint8)
-        else:
+        else:                                   # pad every segment to a 16-byte boundary
             packed = torch.zeros(so[-1], dtype=torch.uint8, device=send.device)
             src = send.view(torch.uint8)
             o = 0
@@ -137,15 +150,16 @@ class P2PAllToAll:
                 nb = int(send_counts[p]) * es
                 packed[so[p]:so[p] + nb] = src[o:o + nb]
                 o += nb
-        self._C.p2p_alltoall(packed, so, buf.peer_ptrs(), dst_off, self.ctas)
+        self._C.p2p_alltoall(packed, so, buf.peer_ptrs(), dst_off, ctas)
         self.barrier()
-        mine = recv_counts_matrix[self.rank]
-        total = sum(int(c) for c in mine)
-        out = torch.empty(total, dtype=send.dtype, device=send.device)
+        total = sum(mine)
         raw = buf.view([self.capacity], torch.uint8)
+        if aligned_recv:                        # padded layout == dense layout: one copy out of the window
+            return raw[:total * es].view(send.dtype).clone()
+        out = torch.empty(total, dtype=send.dtype, device=send.device)
         o_b, o_e = 0, 0
         for s in range(W):
-            n = int(mine[s])
+            n = mine[s]
             if n:
                 out[o_e:o_e + n] = raw[o_b:o_b + n * es].view(send.dtype)
             o_b += self._pad16(n * es)

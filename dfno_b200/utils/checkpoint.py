@@ -150,7 +150,8 @@ def save_checkpoint(model, out_dir: str, epoch: Optional[int] = None, optimizer=
     torch.save(net.state_dict(), path)
     train_state = {
         "epoch": epoch,
-        "partition": tuple(int(s) for s in P.shape),
+        # the grid the *layers* are sharded over (differs from P_x when time/channel workers were folded)
+        "partition": tuple(int(s) for s in getattr(net, "P_work", P).shape),
         "world_ranks": P.world_ranks,
         "optimizer": optimizer.state_dict() if optimizer is not None else None,
         "rng_cpu": torch.get_rng_state(),
@@ -175,7 +176,7 @@ def load_checkpoint(model, out_dir: str, epoch: Optional[int] = None, optimizer=
     info: Dict[str, Any] = {"epoch": epoch}
     if os.path.exists(tpath):
         ts = torch.load(tpath, map_location=map_location, weights_only=False)
-        if tuple(ts["partition"]) != tuple(int(s) for s in P.shape):
+        if tuple(ts["partition"]) != tuple(int(s) for s in getattr(net, "P_work", P).shape):
             raise ValueError(f"checkpoint was written on partition {ts['partition']}, "
                              f"model uses {tuple(P.shape)}; use reshard_checkpoint()")
         if optimizer is not None and ts["optimizer"] is not None:

@@ -72,6 +72,8 @@ def _serial_equiv(rank, ws, grid, cfg, plan, tmp):
 
 CFG_2D = dict(in_shape=[2, 1, 12, 10, 3], nt=8, width=5, modes=(3, 2, 3), blocks=2)
 CFG_3D = dict(in_shape=[1, 2, 8, 9, 8, 2], nt=6, width=4, modes=(2, 3, 2, 3), blocks=2)
+CFG_4D_T = dict(in_shape=[1, 1, 8, 8, 8, 8], nt=8, width=4, modes=(2, 2, 2, 3), blocks=1)
+CFG_3D_8 = dict(in_shape=[1, 1, 8, 8, 8, 2], nt=4, width=4, modes=(2, 2, 2, 2), blocks=1)
 
 
 @pytest.mark.parametrize("ws,grid,cfg,plan", [
@@ -80,6 +82,8 @@ CFG_3D = dict(in_shape=[1, 2, 8, 9, 8, 2], nt=6, width=4, modes=(2, 3, 2, 3), bl
     (4, (1, 1, 1, 4, 1, 1), CFG_3D, "reference"),     # 1 x k pencil: R1/R4 identity
     (4, (1, 1, 1, 4, 1, 1), CFG_3D, "balanced"),
     (2, (2, 1, 1, 1, 1), CFG_2D, "reference"),        # batch (data) parallel axis
+    (4, (1, 1, 1, 1, 1, 4), CFG_4D_T, "reference"),   # time-axis partition (BASELINE cfg4 semantics)
+    (8, (1, 1, 2, 2, 2, 1), CFG_3D_8, "reference"),   # 2x2x2 spatial partition (BASELINE cfg3 topology)
 ])
 def test_distributed_equals_serial(ws, grid, cfg, plan):
     with tempfile.TemporaryDirectory() as tmp:
