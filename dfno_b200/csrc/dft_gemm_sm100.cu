@@ -204,20 +204,35 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ---- coalesced row-major store: TMEM -> fp32 staging rows in smem (a private 32-row
         // slab per warp) -> groups of lanes write whole rows contiguously
         uint8_t* slab = smem + L.stage_off + ((g * 4 + q) * 32) * L.stage_pitch;
-        float* myrow = reinterpret_cast<float*>(slab + lane * L.stage_pitch);
+        uint8_t* myrow = slab + lane * L.stage_pitch;
+        const bool st16 = !p.epi.out_fp32;                       // bf16 output: stage packed bf16
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
           tmem_ld_wait();
+          if (st16) {
+            uint4 u0, u1;
+            u0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+            u0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+            u0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+            u0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+            u1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+            u1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+            u1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+            u1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+            reinterpret_cast<uint4*>(myrow + c0 * 2)[0] = u0;
+            reinterpret_cast<uint4*>(myrow + c0 * 2)[1] = u1;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(myrow + c0)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<uint4*>(myrow + c0 * 4)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
         }
         // the accumulator is drained into smem: release the TMEM stage before the global stores
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[a]);
-        const int vec_per_row = p.N >> 3;                       // 8 outputs (16 B of bf16) per lane
+        const int vec_per_row = p.N >> 3;                       // 8 outputs per lane
         const int rows_per_it = 32 / vec_per_row;               // N = 128 -> 16 lanes per row, 2 rows / instr
         const int lr = lane / vec_per_row, lc = lane % vec_per_row;
         const long long row0 = static_cast<long long>(tile) * kTileM + q * 32;
@@ -238,23 +253,28 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (!okv[u]) continue;
             const int rr = rb + u * rows_per_it;
             const long long grow = row0 + rr;
-            const float* srow = reinterpret_cast<const float*>(slab + rr * L.stage_pitch) + lc * 8;
-            float4 f0 = reinterpret_cast<const float4*>(srow)[0];
-            float4 f1 = reinterpret_cast<const float4*>(srow)[1];
-            float2 t;
-            t = unpack_bf16x2(addv[u].x); f0.x += t.x; f0.y += t.y;
-            t = unpack_bf16x2(addv[u].y); f0.z += t.x; f0.w += t.y;
-            t = unpack_bf16x2(addv[u].z); f1.x += t.x; f1.y += t.y;
-            t = unpack_bf16x2(addv[u].w); f1.z += t.x; f1.w += t.y;
-            if (p.epi.out_fp32) {
+            const uint8_t* srow = slab + rr * L.stage_pitch;
+            if (st16) {
+              uint4 sv = *reinterpret_cast<const uint4*>(srow + lc * 16);
+              if (p.epi.add_src != nullptr) {
+                float2 a, b;
+                a = unpack_bf16x2(sv.x); b = unpack_bf16x2(addv[u].x); sv.x = pack_bf16x2(a.x + b.x, a.y + b.y);
+                a = unpack_bf16x2(sv.y); b = unpack_bf16x2(addv[u].y); sv.y = pack_bf16x2(a.x + b.x, a.y + b.y);
+                a = unpack_bf16x2(sv.z); b = unpack_bf16x2(addv[u].z); sv.z = pack_bf16x2(a.x + b.x, a.y + b.y);
+                a = unpack_bf16x2(sv.w); b = unpack_bf16x2(addv[u].w); sv.w = pack_bf16x2(a.x + b.x, a.y + b.y);
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = sv;
+            } else {
+              float4 f0 = reinterpret_cast<const float4*>(srow + lc * 32)[0];
+              float4 f1 = reinterpret_cast<const float4*>(srow + lc * 32)[1];
+              float2 t;
+              t = unpack_bf16x2(addv[u].x); f0.x += t.x; f0.y += t.y;
+              t = unpack_bf16x2(addv[u].y); f0.z += t.x; f0.w += t.y;
+              t = unpack_bf16x2(addv[u].z); f1.x += t.x; f1.y += t.y;
+              t = unpack_bf16x2(addv[u].w); f1.z += t.x; f1.w += t.y;
               float* o = reinterpret_cast<float*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8;
               reinterpret_cast<float4*>(o)[0] = f0;
               reinterpret_cast<float4*>(o)[1] = f1;
-            } else {
-              uint4 u4;
-              u4.x = pack_bf16x2(f0.x, f0.y); u4.y = pack_bf16x2(f0.z, f0.w);
-              u4.z = pack_bf16x2(f1.x, f1.y); u4.w = pack_bf16x2(f1.z, f1.w);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.epi.peers[0]) + grow * p.epi.ldc + lc * 8) = u4;
             }
           }
         }
@@ -392,7 +412,7 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   uint32_t stage_total = 0;
   if (p.epi.mode == EPI_ROWMAJOR && p.epi.vec_ok && p.N % 8 == 0 && (p.N == 8 || p.N == 16 || p.N == 32 ||
       p.N == 64 || p.N == 128 || p.N == 256)) {
-    const uint32_t pitch = ((p.N + 15) / 16 * 16) * 4 + 16;   // whole 16-column chunks are staged
+    const uint32_t pitch = ((p.N + 15) / 16 * 16) * (p.epi.out_fp32 ? 4 : 2) + 16;   // whole 16-column chunks are staged
     L.stage_pitch = pitch;
   }
   // epilogue groups and TMEM accumulator stages
