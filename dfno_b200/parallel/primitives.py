@@ -365,7 +365,7 @@ def _exchange(x: torch.Tensor, plan: RepartitionPlan, group, device, dtype, matr
         recv.copy_(send)
     elif eng is not None:
         recv = eng.exchange(send, [c * width for c in plan.send_counts],
-                            [[c * width for c in row] for row in matrix])
+                            [[c * width for c in row] for row in matrix], copy=False)   # unpacked right below
     else:
         dist.all_to_all_single(recv, send,
                                [c * width for c in plan.recv_counts],

@@ -125,13 +125,16 @@ class P2PAllToAll:
             mine = [int(c) for c in recv_counts_matrix[self.rank]]
             aligned_recv = all(c * es % 16 == 0 for c in mine)
             per_peer = max(so[p + 1] - so[p] for p in range(W))
-            ctas = max(1, min(32, per_peer // 65536))
+            ctas = max(1, min(16, per_peer // 65536))
             hit = (dst_off, so, aligned_send, mine, aligned_recv, ctas)
             self._cache[key] = hit
         return hit
 
-    def exchange(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts_matrix) -> torch.Tensor:
-        """``send``: flat contiguous tensor whose consecutive pieces of ``send_counts[p]``
+    def exchange(self, send: torch.Tensor, send_counts: Sequence[int], recv_counts_matrix,
+                 copy: bool = True) -> torch.Tensor:
+        """``copy=False`` returns a *view* of the receive window (valid until the exchange after
+        the next one) when the segments are 16-byte multiples -- the caller consumes it at once.
+        ``send``: flat contiguous tensor whose consecutive pieces of ``send_counts[p]``
         elements go to peer ``p``.  ``recv_counts_matrix[d][s]``: elements rank ``s`` sends to
         rank ``d`` (every rank can compute it from the Repartition plans).  Returns a flat
         tensor with the pieces received from rank 0, 1, ... concatenated."""
@@ -155,7 +158,8 @@ class P2PAllToAll:
         total = sum(mine)
         raw = buf.view([self.capacity], torch.uint8)
         if aligned_recv:                        # padded layout == dense layout: one copy out of the window
-            return raw[:total * es].view(send.dtype).clone()
+            window = raw[:total * es].view(send.dtype)
+            return window.clone() if copy else window
         out = torch.empty(total, dtype=send.dtype, device=send.device)
         o_b, o_e = 0, 0
         for s in range(W):
