@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the e2e step from a CUDA graph")
     return ap.parse_args()
 
 
@@ -197,13 +198,14 @@ def main():
     # ---- end to end through the public Trainer API: pinned host batch in, loss out
     e2e = None
     if not args.no_e2e:
-        tr = d.Trainer(net, crit, opt, device=dev)
-        for _ in range(2):
+        tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=args.graph)
+        for _ in range(3):
             tr.step(x_host, y_host, next_batch=(x_host, y_host))
         e2e_ms = timed(lambda: tr.step(x_host, y_host, next_batch=(x_host, y_host)), args.steps)
         e2e = {"value": args.batch * 1000.0 / (e2e_ms / args.steps), "unit": "samples/s",
                "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": tr.h2d_bytes,
                "d2h_bytes_per_step": tr.d2h_bytes,
+               "cuda_graph": bool(tr._graph is not None),
                "how": "Trainer.step(): pinned host batch -> async H2D (double buffered) -> fwd+loss+bwd+Adam -> loss D2H"}
 
     if rank == 0:

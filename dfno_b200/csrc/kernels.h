@@ -41,8 +41,8 @@ const char* spectral_mix_bwd(const void* x, const float* w, const void* dy, void
 
 // fused Adam over one flat fp32 parameter buffer (decoupled=0: L2 weight decay like torch.optim.Adam)
 const char* adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, float bias1, float bias2, float grad_scale, int num_sms,
-                      cudaStream_t s);
+                      float eps, float weight_decay, float bias1, float bias2, float grad_scale, const float* step_dev,
+                      int num_sms, cudaStream_t s);
 
 // cross-GPU flag barrier over NVLink-mapped signal pads: every rank bumps its slot on each
 // peer to `epoch`, then waits until all of its own slots reached `epoch`.

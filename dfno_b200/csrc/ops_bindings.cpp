@@ -103,15 +103,18 @@ void spectral_mix_bwd(const at::Tensor& x, const at::Tensor& w, const at::Tensor
 }
 
 void adam_step(at::Tensor& p, const at::Tensor& g, at::Tensor& m, at::Tensor& v, double lr, double beta1, double beta2,
-               double eps, double weight_decay, int64_t step, double grad_scale) {
+               double eps, double weight_decay, int64_t step, double grad_scale,
+               const c10::optional<at::Tensor>& step_dev) {
   TORCH_CHECK(p.numel() == g.numel() && p.numel() == m.numel() && p.numel() == v.numel(), "adam: size mismatch");
   c10::cuda::CUDAGuard guard(p.device());
+  if (step < 1) step = 1;
   const double bias1 = 1.0 - std::pow(beta1, static_cast<double>(step));
   const double bias2 = 1.0 - std::pow(beta2, static_cast<double>(step));
   check(dfno::adam_step(fptr_mut(p), fptr(g), fptr_mut(m), fptr_mut(v), p.numel(), static_cast<float>(lr),
                         static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(eps),
                         static_cast<float>(weight_decay), static_cast<float>(bias1), static_cast<float>(bias2),
-                        static_cast<float>(grad_scale), sm_count(), cur_stream()), "adam_step");
+                        static_cast<float>(grad_scale), step_dev ? fptr(*step_dev) : nullptr, sm_count(), cur_stream()),
+        "adam_step");
 }
 
 void p2p_barrier(const std::vector<int64_t>& flag_ptrs, int64_t rank, int64_t epoch, double timeout_s) {
@@ -186,7 +189,9 @@ void register_ops(pybind11::module& m) {
   m.def("bypass_bwd_tc", &bypass_bwd_tc);
   m.def("spectral_mix_fwd", &spectral_mix_fwd);
   m.def("spectral_mix_bwd", &spectral_mix_bwd);
-  m.def("adam_step", &adam_step);
+  m.def("adam_step", &adam_step, py::arg("p"), py::arg("g"), py::arg("m"), py::arg("v"), py::arg("lr"), py::arg("beta1"),
+        py::arg("beta2"), py::arg("eps"), py::arg("weight_decay"), py::arg("step"), py::arg("grad_scale"),
+        py::arg("step_dev") = c10::nullopt);
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_allreduce_small", &p2p_allreduce_small);
   m.def("p2p_alltoall", &p2p_alltoall);

@@ -11,7 +11,12 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
             long long n4, float* __restrict__ ps, const float* __restrict__ gs, float* __restrict__ ms,
             float* __restrict__ vs, int tail, float lr, float b1, float b2, float eps, float wd, float bias1,
-            float bias2, float gscale) {
+            float bias2, float gscale, const float* __restrict__ step_dev) {
+  if (step_dev != nullptr) {                 // step count read from device memory (CUDA-graph replay)
+    const float t = *step_dev;
+    bias1 = 1.f - powf(b1, t);
+    bias2 = 1.f - powf(b2, t);
+  }
   const float step = lr / bias1;
   const float inv_sqrt_b2 = rsqrtf(bias2);
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
@@ -36,8 +41,8 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
 }  // namespace
 
 const char* adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, float bias1, float bias2, float grad_scale, int num_sms,
-                      cudaStream_t s) {
+                      float eps, float weight_decay, float bias1, float bias2, float grad_scale, const float* step_dev,
+                      int num_sms, cudaStream_t s) {
   if (n <= 0) return nullptr;
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) % 16)
@@ -51,7 +56,7 @@ const char* adam_step(float* p, const float* g, float* m, float* v, long long n,
   adam_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), n4, p + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, tail, lr, beta1, beta2, eps,
-      weight_decay, bias1, bias2, grad_scale);
+      weight_decay, bias1, bias2, grad_scale, step_dev);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -35,8 +35,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // GPU of the box forever -- the reference has exactly this failure mode with MPI (SURVEY.md
 // 5.3).  The spin is bounded: after `timeout_ns` the slot that is late is recorded in
 // my_flags[16 + r] and the kernel traps, so the hang surfaces as a CUDA error on this rank.
-__global__ void p2p_barrier_kernel(PeerFlags peers, uint32_t* my_flags, int rank, int world, uint32_t epoch,
+__global__ void p2p_barrier_kernel(PeerFlags peers, uint32_t* my_flags, int rank, int world, uint32_t epoch_arg,
                                    unsigned long long timeout_ns) {
+  // The epoch lives in device memory (my_flags[32]) and is bumped by the kernel itself, so the
+  // launch carries no step-dependent argument and can be replayed from a CUDA graph.  Every
+  // rank executes the same barrier sequence, hence the counters agree.  epoch_arg != 0 overrides.
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    const uint32_t e = epoch_arg ? epoch_arg : my_flags[32] + 1;
+    my_flags[32] = e;
+    s_epoch = e;
+  }
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
   const int r = threadIdx.x;
   if (r < world) {
     __threadfence_system();

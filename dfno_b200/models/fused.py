@@ -650,6 +650,8 @@ class FusedAdam:
         self.m = torch.zeros_like(model.theta.data)
         self.v = torch.zeros_like(model.theta.data)
         self.step_count = 0
+        # the step counter also lives on the device so a captured CUDA graph can replay the update
+        self.step_dev = torch.zeros(1, device=model.theta.device, dtype=torch.float32)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         if set_to_none:
@@ -662,8 +664,10 @@ class FusedAdam:
         if g is None:
             return
         self.step_count += 1
+        self.step_dev += 1.0
         self.model._C.adam_step(self.model.theta.data, g.contiguous(), self.m, self.v, self.lr, self.betas[0],
-                                self.betas[1], self.eps, self.weight_decay, self.step_count, grad_scale)
+                                self.betas[1], self.eps, self.weight_decay, self.step_count, grad_scale,
+                                self.step_dev)
 
     def state_dict(self):
         return {"m": self.m, "v": self.v, "step": self.step_count, "lr": self.lr, "betas": self.betas,
@@ -672,4 +676,5 @@ class FusedAdam:
     def load_state_dict(self, sd) -> None:
         self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
         self.step_count = int(sd["step"])
+        self.step_dev.fill_(float(self.step_count))
         self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]

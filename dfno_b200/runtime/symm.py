@@ -77,8 +77,8 @@ class PeerBarrier:
     def __call__(self) -> None:
         if self.world <= 1:
             return
-        self.epoch += 1
-        self.pad._C.p2p_barrier(self.pad.peer_ptrs(), self.rank, self.epoch, self.timeout_s)
+        self.epoch += 1                       # host-side count (diagnostics); the kernel keeps its own
+        self.pad._C.p2p_barrier(self.pad.peer_ptrs(), self.rank, 0, self.timeout_s)
 
     def late_peers(self):
         """After a barrier timeout: ``{peer: epoch}`` of the slots that never arrived."""

@@ -16,7 +16,7 @@ __all__ = ["Trainer"]
 
 class Trainer:
     def __init__(self, model, criterion, optimizer, device: Optional[torch.device] = None,
-                 target_dtype: Optional[torch.dtype] = None):
+                 target_dtype: Optional[torch.dtype] = None, cuda_graph: bool = False):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.cuda = self.device.type == "cuda"
@@ -29,6 +29,12 @@ class Trainer:
         self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory() if self.cuda else torch.zeros(())
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        # CUDA-graph replay of the whole step (forward, loss, backward, optimizer): one launch per
+        # step instead of a few hundred.  Falls back to eager execution if capture is not possible.
+        self.cuda_graph = bool(cuda_graph) and self.cuda
+        self._graph = None
+        self._graph_failed = False
+        self.graph_kernel_launches = 0
 
     # -------------------------------------------------------------------- data movement
     def _upload(self, x_host: torch.Tensor, y_host: torch.Tensor):
@@ -69,11 +75,7 @@ class Trainer:
             torch.cuda.current_stream(self.device).wait_event(ev)
         if next_batch is not None:
             self.prefetch(*next_batch)
-        self.optimizer.zero_grad(set_to_none=True)
-        y_hat = self.model(xd)
-        loss = self.criterion(y_hat, yd)
-        loss.backward()
-        self.optimizer.step()
+        loss = self._graphed(xd, yd) if (self.cuda_graph and not self._graph_failed) else self._eager(xd, yd)
         if self.cuda:
             self._loss_host.copy_(loss.detach(), non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
@@ -81,6 +83,51 @@ class Trainer:
             return float(self._loss_host)
         self.d2h_bytes = 0
         return float(loss.detach())
+
+    def _eager(self, xd: torch.Tensor, yd: torch.Tensor) -> torch.Tensor:
+        self.optimizer.zero_grad(set_to_none=True)
+        y_hat = self.model(xd)
+        loss = self.criterion(y_hat, yd)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def _graphed(self, xd: torch.Tensor, yd: torch.Tensor) -> torch.Tensor:
+        if self._graph is None:
+            try:
+                self._gx, self._gy = torch.empty_like(xd), torch.empty_like(yd)
+                self._gx.copy_(xd); self._gy.copy_(yd)
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):                 # warm-up off the capturing stream
+                    for _ in range(2):
+                        self._eager(self._gx, self._gy)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                counter = getattr(self.model, "_C", None)
+                c0 = getattr(counter, "count", 0)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._gloss = self._eager(self._gx, self._gy).detach()
+                self.graph_kernel_launches = getattr(counter, "count", 0) - c0
+                self._graph = graph
+                self._graph_steps_py = getattr(self.optimizer, "step_count", None)
+            except Exception as e:                            # noqa: BLE001 - capture is an optimisation
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
+                              f"running eagerly")
+                self._graph_failed = True
+                torch.cuda.synchronize(self.device)
+                return self._eager(xd, yd)
+        self._gx.copy_(xd, non_blocking=True)
+        self._gy.copy_(yd, non_blocking=True)
+        self._graph.replay()
+        if hasattr(self.optimizer, "step_count"):
+            self.optimizer.step_count += 1                    # host mirror of the device-side counter
+        counter = getattr(self.model, "_C", None)
+        if hasattr(counter, "count"):
+            counter.count += self.graph_kernel_launches
+        return self._gloss
 
     @torch.no_grad()
     def evaluate(self, x_host: torch.Tensor, y_host: torch.Tensor) -> float:

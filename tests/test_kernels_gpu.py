@@ -14,7 +14,9 @@ def C_():
 
 
 def rel(a, b):
-    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+    a = torch.view_as_real(a) if a.is_complex() else a
+    b = torch.view_as_real(b) if b.is_complex() else b
+    return float((a.detach().float() - b.detach().float()).norm() / b.detach().float().norm().clamp_min(1e-30))
 
 
 def bf(t):
