@@ -218,14 +218,15 @@ class AllSumReduce(nn.Module):
 
 
 class ZeroVolumeCorrectorFunction(torch.autograd.Function):
-    """Turn a zero-volume (or NaN-from-empty-mean) result into a scalar 0 so every rank
+    """Turn a zero-volume result into a scalar 0 so every rank
     can call ``.backward()``; the backward hands the original empty shape back.
     (contract: SURVEY.md §2.2 E7, used at ``/root/reference/dfno/loss.py:35``)."""
 
     @staticmethod
     def forward(ctx, x):
         ctx.in_shape = x.shape
-        ctx.was_empty = x.numel() == 0 or bool(torch.isnan(x).all())
+        # decided from the shape alone: no device->host sync (keeps the step CUDA-graph capturable)
+        ctx.was_empty = x.numel() == 0
         if ctx.was_empty:
             return x.new_zeros(())
         return x.clone()
