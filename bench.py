@@ -150,7 +150,7 @@ def main():
         params = [p for p in net.parameters() if p.numel() > 0]
         opt = torch.optim.Adam(params, lr=1e-3)
         in_dtype = torch.bfloat16
-    crit = d.DistributedRelativeLpLoss(P_x)
+    crit = d.DistributedRelativeLpLoss(P_x, engine=net if args.impl == "fused" else None)
 
     Yl = G // N
     x_host = torch.randn(args.batch, 1, G, Yl, G, 1, dtype=in_dtype).pin_memory()

@@ -570,13 +570,24 @@ class FusedDistributedFNO(nn.Module):
         pl = self.plan
         small = self.grad_flat[:pl.n_small]
         if self.use_p2p:
-            stage = self.sym_small.view([pl.n_small], torch.float32)
-            self.barrier()                       # previous readers are done with the staging buffer
-            stage.copy_(small)
-            self.barrier()                       # every rank's contribution is visible
-            self._C.p2p_allreduce_small(self.sym_small.peer_ptrs(), small, pl.n_small, self.rank)
+            self.allreduce_small_(small)
         else:
             dist.all_reduce(small, group=self.P_x.group)
+
+    def allreduce_small_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum of a small contiguous fp32 vector over the pencil through peer memory
+        (no NCCL; CUDA-graph capturable).  Every rank gets the bitwise identical result."""
+        if self.world <= 1:
+            return t
+        n = t.numel()
+        if n > self.plan.n_small or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("allreduce_small_ takes a contiguous fp32 vector no longer than the pointwise segment")
+        stage = self.sym_small.view([n], torch.float32)
+        self.barrier()                           # previous readers are done with the staging buffer
+        stage.copy_(t.view(-1))
+        self.barrier()                           # every rank's contribution is visible
+        self._C.p2p_allreduce_small(self.sym_small.peer_ptrs(), t.view(-1), n, self.rank)
+        return t
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return _FusedFn.apply(x, self.theta, self)

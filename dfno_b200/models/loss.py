@@ -24,15 +24,58 @@ def _acc_dtype(t: torch.Tensor) -> torch.dtype:
     return torch.float32 if t.dtype in (torch.bfloat16, torch.float16) else t.dtype
 
 
+class _EngineReducedLoss(torch.autograd.Function):
+    """Relative-L2 / MSE with the cross-rank sums done by the fused engine's peer-memory
+    all-reduce: no NCCL call, CUDA-graph capturable, and the value is valid on *every* rank."""
+
+    @staticmethod
+    def forward(ctx, y_hat, y, engine, kind):
+        B = y_hat.shape[0]
+        d = y_hat.float() - y.float()
+        if kind == "rel2":
+            part = torch.cat([(d * d).reshape(B, -1).sum(1), (y.float() * y.float()).reshape(B, -1).sum(1)])
+        else:
+            part = torch.stack([(d * d).sum(), d.new_tensor(float(d.numel()))])
+        tot = engine.allreduce_small_(part.contiguous())
+        if kind == "rel2":
+            num, den = tot[:B].sqrt(), tot[B:].sqrt()
+            out = (num / den).mean()
+            ctx.save_for_backward(d, num, den)
+        else:
+            out = tot[0] / tot[1]
+            ctx.save_for_backward(d, tot)
+        ctx.kind, ctx.in_dtype = kind, y_hat.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.kind == "rel2":
+            d, num, den = ctx.saved_tensors
+            B = d.shape[0]
+            scale = (g / B) / (num * den).clamp_min(1e-30)
+            grad = d * scale.view(B, *([1] * (d.dim() - 1)))
+        else:
+            d, tot = ctx.saved_tensors
+            grad = d * (2.0 * g / tot[1])
+        return grad.to(ctx.in_dtype), None, None, None
+
+
 class DistributedRelativeLpLoss(nn.Module):
-    def __init__(self, P_x: Partition, p: float = 2):
+    """``engine=<FusedDistributedFNO>`` (p = 2 only) routes the two scalar reductions through the
+    engine's NVLink peer-memory all-reduce instead of NCCL; the loss is then valid on all ranks."""
+
+    def __init__(self, P_x: Partition, p: float = 2, engine=None):
         super().__init__()
         self.P_x, self.p = P_x, p
+        self.engine = engine if (engine is not None and getattr(engine, "world", 1) > 1 and p == 2
+                                 and getattr(engine, "use_p2p", False)) else None
         self.P_0 = create_root_partition(P_x)
         self.sr0 = SumReduce(P_x, self.P_0)
         self.sr1 = SumReduce(P_x, self.P_0)
 
     def forward(self, y_hat: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.engine is not None:
+            return _EngineReducedLoss.apply(y_hat, y, self.engine, "rel2")
         B = y_hat.shape[0]
         acc = _acc_dtype(y_hat)
         d = (y_hat.to(acc) - y.to(acc)).reshape(B, -1)
@@ -50,13 +93,17 @@ class DistributedRelativeLpLoss(nn.Module):
 
 
 class DistributedMSELoss(nn.Module):
-    def __init__(self, P_x: Partition):
+    def __init__(self, P_x: Partition, engine=None):
         super().__init__()
         self.P_x = P_x
+        self.engine = engine if (engine is not None and getattr(engine, "world", 1) > 1
+                                 and getattr(engine, "use_p2p", False)) else None
         self.P_0 = create_root_partition(P_x)
         self.sr = SumReduce(P_x, self.P_0)
 
     def forward(self, y_hat: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.engine is not None:
+            return _EngineReducedLoss.apply(y_hat, y, self.engine, "mse")
         acc = _acc_dtype(y_hat)
         d = y_hat.to(acc) - y.to(acc)
         part = torch.stack([(d * d).sum(), d.new_tensor(float(d.numel()))])

@@ -33,7 +33,8 @@ def _worker(rank, ws, cfg, use_p2p):
     lo_o, hi_o = shard_bounds(oshape, P_x.shape, P_x.index)
     xl, tl = xg[assemble_slices(lo, hi)].contiguous(), tg[assemble_slices(lo_o, hi_o)].contiguous()
 
-    crit = d.DistributedMSELoss(P_x)
+    crit = d.DistributedMSELoss(P_x, engine=net)          # peer-memory reduction when use_p2p, NCCL otherwise
+    rel_p2p, rel_nccl = d.DistributedRelativeLpLoss(P_x, engine=net), d.DistributedRelativeLpLoss(P_x)
     y_ref = ref(xg)
     ((y_ref - tg) ** 2).mean().backward()
     res = {}
@@ -43,6 +44,9 @@ def _worker(rank, ws, cfg, use_p2p):
         loss = crit(y, tl)
         loss.backward()
     want = y_ref.detach()[assemble_slices(lo_o, hi_o)]
+    la, lb = rel_p2p(y.detach(), tl), rel_nccl(y.detach(), tl)
+    if P_0.active:
+        assert abs(float(la) - float(lb)) < 1e-5 * abs(float(lb)), (float(la), float(lb))
     res["fwd"] = float((y.detach() - want).norm() / want.norm())
     if P_0.active:
         res["loss"] = abs(float(loss) - float(((y_ref - tg) ** 2).mean())) / float(((y_ref - tg) ** 2).mean())
