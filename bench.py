@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the e2e step from a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -157,12 +157,11 @@ def main():
     y_host = torch.randn(args.batch, 1, G, Yl, G, T, dtype=torch.float32).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
+    use_graph = args.impl == "fused" and not args.no_graph
+    tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=use_graph)
+
     def step_device():
-        opt.zero_grad(set_to_none=True)
-        loss = crit(net(x_dev), y_dev)
-        loss.backward()
-        opt.step()
-        return loss
+        return tr.step_on_device(x_dev, y_dev)
 
     def sync_all():
         if N > 1:
@@ -198,7 +197,6 @@ def main():
     # ---- end to end through the public Trainer API: pinned host batch in, loss out
     e2e = None
     if not args.no_e2e:
-        tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=args.graph)
         for _ in range(3):
             tr.step(x_host, y_host, next_batch=(x_host, y_host))
         e2e_ms = timed(lambda: tr.step(x_host, y_host, next_batch=(x_host, y_host)), args.steps)
@@ -220,6 +218,7 @@ def main():
                        "l2": "per-step working set (>=0.2 GB/rank/block activations) exceeds the 126 MB L2; no flush needed",
                        "step": "forward + DistributedRelativeLpLoss + backward + Adam"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "cuda_graph": bool(tr._graph is not None),
         }
         print(json.dumps(out))
     if dist.is_initialized():

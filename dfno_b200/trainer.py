@@ -84,6 +84,11 @@ class Trainer:
         self.d2h_bytes = 0
         return float(loss.detach())
 
+    def step_on_device(self, xd: torch.Tensor, yd: torch.Tensor) -> torch.Tensor:
+        """One optimisation step on a batch that already lives on the device; returns the loss
+        as a device tensor (no host synchronisation).  Replays the captured graph when enabled."""
+        return self._graphed(xd, yd) if (self.cuda_graph and not self._graph_failed) else self._eager(xd, yd)
+
     def _eager(self, xd: torch.Tensor, yd: torch.Tensor) -> torch.Tensor:
         self.optimizer.zero_grad(set_to_none=True)
         y_hat = self.model(xd)
