@@ -60,7 +60,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -78,6 +78,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        if not self.lines:                       # region shorter than one sampling period: one direct query
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+                self.lines = [ln.strip() for ln in out.stdout.splitlines() if ln.strip()]
+            except Exception:
+                pass
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -181,11 +188,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                          # covers warm-up + timed region (identical load)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
     counter = getattr(net, "_C", None)
     c0 = counter.count if hasattr(counter, "count") else 0
     total_ms = timed(step_device, args.steps)
