@@ -34,7 +34,8 @@ static constexpr int kTileM = 128;
 static constexpr int kBlockK = 64;                 // bf16 elements per 128-byte swizzle row
 static constexpr int kMaxThreads = 64 + 128 * 4;   // warp0 TMA, warp1 MMA, then E groups of 4 epilogue warps
 static constexpr uint32_t kTmemCols = 512;
-static constexpr int kMaxStages = 4;
+static constexpr int kMaxStages = 8;                // A-tile ring depth: bytes in flight per SM must cover
+                                                    // HBM latency x bandwidth share (~45 KB), small tiles need more stages
 static constexpr int kMaxAcc = 8;                  // TMEM accumulator stages
 
 struct SmemLayout {
@@ -82,13 +83,13 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + L.b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + L.stages * L.a_tile_bytes);
-  uint64_t* full = bars;                      // [4]   TMA -> MMA
-  uint64_t* empty = bars + 4;                 // [4]   MMA -> TMA
-  uint64_t* tfull = bars + 8;                 // [8]   MMA -> epilogue
-  uint64_t* tempty = bars + 16;               // [8]   epilogue -> MMA
-  uint64_t* bfull = bars + 24;                // [1]   B resident
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
-  long long* s_coloff = reinterpret_cast<long long*>(bars + 32);        // [128] pair -> element offset
+  uint64_t* full = bars;                      // [8]   TMA -> MMA
+  uint64_t* empty = bars + 8;                 // [8]   MMA -> TMA
+  uint64_t* tfull = bars + 16;                // [8]   MMA -> epilogue
+  uint64_t* tempty = bars + 24;               // [8]   epilogue -> MMA
+  uint64_t* bfull = bars + 32;                // [1]   B resident
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 33);
+  long long* s_coloff = reinterpret_cast<long long*>(bars + 40);        // [128] pair -> element offset
   float* s_vec = reinterpret_cast<float*>(s_coloff + 128);              // [512] EPI_HEAD vectors
   uint8_t* s_colpeer = reinterpret_cast<uint8_t*>(s_vec + 512);         // [128] pair -> peer
 
