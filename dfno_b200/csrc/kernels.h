@@ -17,6 +17,9 @@ const char* lift_fwd(const void* x, int x_is_bf16, const float* W1, const float*
 const char* lift_bwd(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
                      const float* b2, const void* dh, float* gW1, float* gb1, float* gW2, float* gb2,
                      LiftDims d, int num_sms, cudaStream_t s);
+// strided permutation of 32-bit words: dst walked in mixed-radix order (innermost digit first, strides in words)
+const char* permute_u32(const void* src, void* dst, int nd, const int* size, const long long* sstr,
+                        const long long* dstr, int num_sms, cudaStream_t s);
 // device GELU / GELU' evaluated on a vector (accuracy probe for the tests)
 const char* gelu_probe(const float* x, float* y, float* dy, long long n, cudaStream_t s);
 // S = X*Y*T*Z elements per (b, c) slab.  out / out_cl may be null.

@@ -156,6 +156,17 @@ void kreduce_gemm(const at::Tensor& A, int64_t lda, int64_t Ma, const at::Tensor
                            D.stride(0), sm_count(), cur_stream()), "kreduce_gemm");
 }
 
+void permute_u32(const at::Tensor& src, at::Tensor& dst, const std::vector<int64_t>& size,
+                 const std::vector<int64_t>& sstr, const std::vector<int64_t>& dstr) {
+  TORCH_CHECK(size.size() == sstr.size() && size.size() == dstr.size() && !size.empty() && size.size() <= 6,
+              "permute_u32: 1..6 matching digits");
+  c10::cuda::CUDAGuard guard(src.device());
+  int sz[6]; long long ss[6], ds[6];
+  for (size_t i = 0; i < size.size(); ++i) { sz[i] = static_cast<int>(size[i]); ss[i] = sstr[i]; ds[i] = dstr[i]; }
+  check(dfno::permute_u32(src.data_ptr(), dst.data_ptr(), static_cast<int>(size.size()), sz, ss, ds, sm_count(),
+                          cur_stream()), "permute_u32");
+}
+
 std::vector<at::Tensor> gelu_probe(const at::Tensor& x) {
   c10::cuda::CUDAGuard guard(x.device());
   at::Tensor y = at::empty_like(x), dy = at::empty_like(x);
@@ -198,4 +209,5 @@ void register_ops(pybind11::module& m) {
   m.def("kreduce_gemm", &kreduce_gemm);
   m.def("head_bwd", &head_bwd);
   m.def("gelu_probe", &gelu_probe);
+  m.def("permute_u32", &permute_u32);
 }

@@ -337,6 +337,32 @@ __global__ void gelu_probe_kernel(const float* __restrict__ x, float* __restrict
   if (i < n) { y[i] = gelu_erf(x[i]); dy[i] = gelu_erf_grad(x[i]); }
 }
 
+// Generic strided permutation of 32-bit words (one (re, im) bf16 pair each): dst is walked in its
+// own mixed-radix order (innermost digit first), the same digits address src through src_strides.
+// Used on the receiving side of the fused pencil transposes: peers deposit their contribution as
+// one long contiguous run per source rank (NVLink-friendly), this kernel interleaves the runs into
+// the K-major layout the next GEMM stage reads.  The tensors are the *truncated* spectra, a few MB.
+struct PermuteDesc { int nd; int size[6]; long long sstr[6]; long long dstr[6]; };
+
+__global__ void __launch_bounds__(256)
+permute_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long long total, PermuteDesc d) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i, so = 0, dof = 0;
+#pragma unroll
+    for (int l = 0; l < 6; ++l) {
+      if (l < d.nd) {
+        const long long q = r / d.size[l];
+        const long long dig = r - q * d.size[l];
+        r = q;
+        so += dig * d.sstr[l];
+        dof += dig * d.dstr[l];
+      }
+    }
+    dst[dof] = src[so];
+  }
+}
+
 int grid_for(long long work_items, int threads, int num_sms, int per_sm) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms) * per_sm;
@@ -348,6 +374,28 @@ int grid_for(long long work_items, int threads, int num_sms, int per_sm) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+const char* permute_u32(const void* src, void* dst, int nd, const int* size, const long long* sstr,
+                        const long long* dstr, int num_sms, cudaStream_t s) {
+  if (nd < 1 || nd > 6) return "permute_u32: 1..6 digits";
+  PermuteDesc d;
+  d.nd = nd;
+  long long total = 1;
+  for (int i = 0; i < 6; ++i) {
+    d.size[i] = i < nd ? size[i] : 1;
+    d.sstr[i] = i < nd ? sstr[i] : 0;
+    d.dstr[i] = i < nd ? dstr[i] : 0;
+    total *= d.size[i];
+  }
+  if (total <= 0) return nullptr;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  permute_u32_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const uint32_t*>(src),
+                                                              static_cast<uint32_t*>(dst), total, d);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 const char* gelu_probe(const float* x, float* y, float* dy, long long n, cudaStream_t s) {
   gelu_probe_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, y, dy, n);
   cudaError_t e = cudaGetLastError();

@@ -183,20 +183,41 @@ class EnginePlan:
         self.num_blocks = num_blocks
 
     # ---------------------------------------------------------------- stage descriptors
-    def chain(self) -> List[dict]:
-        """The nine GEMM stages of one spectral convolution (forward *or* adjoint: only the
-        operator matrices and the end buffers differ).  Strides in bf16 elements."""
+    def chain(self, staged: bool = False) -> List[dict]:
+        """The GEMM stages of one spectral convolution (forward *or* adjoint: only the operator
+        matrices and the end buffers differ).  Strides in bf16 elements.
+
+        ``staged=True`` (multi-GPU) changes how the two pencil transposes cross NVLink: instead of
+        interleaving directly into the consumer layout (64- / 40-byte runs per destination row)
+        every source rank deposits its contribution as long contiguous runs into a per-source
+        block of a staging buffer (``S1s`` / ``T1s``, >= 512-byte runs), and a tiny local
+        permutation (``permS1`` / ``permT1``) produces the K-major layout of the next stage."""
         BC, X, Y, Z, T = self.BC, self.X, self.Y, self.Z, self.T
         Yl, KX, KY, KZ, kzl, mt, mtp = self.Yl, self.KX, self.KY, self.KZ, self.kzl, self.mt, self.mtp
+        P, r = self.world, self.rank
         m_loc = kzl * mt
         st = []
-        st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
-                       scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * T), (BC * X, KZ * Yl * T * 2)],
-                                           cols=(KZ, Yl * T * 2, 0))))
-        st.append(dict(name="G1b", src="Z1", dst="S1", M=BC * X * KZ * Yl, K=2 * T, lda=2 * T, N=2 * mt, op="G1b",
-                       scatter=ScatterSpec(rows=[(Yl, 2), (KZ, mt * X * Y * 2), (X, Y * 2), (BC, m_loc * X * Y * 2)],
-                                           cols=(mt, X * Y * 2, 0), peer=("row", 1, kzl), base_off=self.y_off * 2),
-                       peer_dst=True, barrier_after=True))
+        if not staged:
+            st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
+                           scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * T), (BC * X, KZ * Yl * T * 2)],
+                                               cols=(KZ, Yl * T * 2, 0))))
+            st.append(dict(name="G1b", src="Z1", dst="S1", M=BC * X * KZ * Yl, K=2 * T, lda=2 * T, N=2 * mt, op="G1b",
+                           scatter=ScatterSpec(rows=[(Yl, 2), (KZ, mt * X * Y * 2), (X, Y * 2), (BC, m_loc * X * Y * 2)],
+                                               cols=(mt, X * Y * 2, 0), peer=("row", 1, kzl), base_off=self.y_off * 2),
+                           peer_dst=True, barrier_after=True))
+        else:
+            st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
+                           scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * T), (X, Yl * 2 * T), (BC, KZ * X * Yl * 2 * T)],
+                                               cols=(KZ, X * Yl * 2 * T, 0))))
+            st.append(dict(name="G1b", src="Z1", dst="S1s", M=BC * KZ * X * Yl, K=2 * T, lda=2 * T, N=2 * mt, op="G1b",
+                           scatter=ScatterSpec(rows=[(Yl, 2), (X, Yl * 2), (KZ, mt * P * X * Yl * 2),
+                                                     (BC, m_loc * P * X * Yl * 2)],
+                                               cols=(mt, P * X * Yl * 2, 0), peer=("row", 2, kzl),
+                                               base_off=r * X * Yl * 2),
+                           peer_dst=True, barrier_after=True))
+            # S1s[a=(bc,kzl,kt), r_src, x, y_loc] -> S1[a, x, (r_src, y_loc)]   (32-bit words = complex pairs)
+            st.append(dict(name="permS1", src="S1s", dst="S1", size=[Yl, P, X, BC * m_loc],
+                           sstr=[1, X * Yl, Yl, P * X * Yl], dstr=[1, Yl, Y, X * Y]))
         st.append(dict(name="G2", src="S1", dst="S2", M=BC * m_loc * X, K=2 * Y, lda=2 * Y, N=2 * KY, op="G2",
                        scatter=ScatterSpec(rows=[(X, 2), (BC * m_loc, KY * X * 2)], cols=(KY, X * 2, 0))))
         st.append(dict(name="G3", src="S2", dst="S3", M=BC * m_loc * KY, K=2 * X, lda=2 * X, N=2 * KX, op="G3",
@@ -205,12 +226,24 @@ class EnginePlan:
         st.append(dict(name="iG3", src="S4", dst="T2", M=BC * m_loc * KY, K=2 * KX, lda=2 * KX, N=2 * X, op="iG3",
                        scatter=ScatterSpec(rows=[(KY, 2), (m_loc, KY * 2), (BC, X * m_loc * KY * 2)],
                                            cols=(X, m_loc * KY * 2, 0))))
-        st.append(dict(name="iG2", src="T2", dst="T1", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
-                       scatter=ScatterSpec(rows=[(mt, 2), (kzl, mtp * 2), (X, Yl * KZ * mtp * 2),
-                                                 (BC, X * Yl * KZ * mtp * 2)],
-                                           cols=(Yl, KZ * mtp * 2, 0), peer=("col", Yl),
-                                           base_off=self.kz_off * mtp * 2),
-                       peer_dst=True, barrier_after=True))
+        if not staged:
+            st.append(dict(name="iG2", src="T2", dst="T1", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
+                           scatter=ScatterSpec(rows=[(mt, 2), (kzl, mtp * 2), (X, Yl * KZ * mtp * 2),
+                                                     (BC, X * Yl * KZ * mtp * 2)],
+                                               cols=(Yl, KZ * mtp * 2, 0), peer=("col", Yl),
+                                               base_off=self.kz_off * mtp * 2),
+                           peer_dst=True, barrier_after=True))
+        else:
+            st.append(dict(name="iG2", src="T2", dst="T1s", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
+                           scatter=ScatterSpec(rows=[(mt, 2), (kzl, mt * 2), (X, m_loc * 2),
+                                                     (BC, P * Yl * X * m_loc * 2)],
+                                               cols=(Yl, X * m_loc * 2, 0), peer=("col", Yl),
+                                               base_off=r * Yl * X * m_loc * 2),
+                           peer_dst=True, barrier_after=True))
+            # T1s[bc, r_src, y_loc, x, kzl, kt] -> T1[bc, x, y_loc, (r_src, kzl), kt (pitch mtp)]
+            st.append(dict(name="permT1", src="T1s", dst="T1", size=[mt, kzl, P, Yl, X, BC],
+                           sstr=[1, mt, Yl * X * m_loc, X * m_loc, m_loc, P * Yl * X * m_loc],
+                           dstr=[1, mtp, kzl * mtp, KZ * mtp, Yl * KZ * mtp, X * Yl * KZ * mtp]))
         st.append(dict(name="iG1b", src="T1", dst="U", M=BC * X * Yl * KZ, K=2 * mt, lda=2 * mtp, N=2 * T, op="iG1b",
                        scatter=ScatterSpec(rows=[(KZ, 2), (BC * X * Yl, T * KZ * 2)], cols=(T, KZ * 2, 0))))
         st.append(dict(name="iG1a", src="U", dst="dst", M=BC * X * Yl * T, K=2 * KZ, lda=2 * KZ, N=Z, op="iG1a",
@@ -343,7 +376,13 @@ class FusedDistributedFNO(nn.Module):
         }
         self._saved: Dict[str, torch.Tensor] = {}
         self._train_bufs_ready = False
-        self.chain_desc = pl.chain()
+        import os as _os0
+        self.staged_scatter = self.world > 1 and _os0.environ.get("DFNO_STAGED_SCATTER", "0") != "0"
+        self.chain_desc = pl.chain(staged=self.staged_scatter)
+        if self.staged_scatter:            # peers write the staging blocks; S1 / T1 become local buffers
+            self.ws["S1s"], self.ws["T1s"] = self.ws["S1"], self.ws["T1"]
+            self.ws["S1"] = torch.empty(pl.n_S1, **bf)
+            self.ws["T1"] = torch.zeros(pl.n_T1, **bf)
         import os as _os
         self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and _os.environ.get("DFNO_TC_BYPASS", "1") != "0")
 
@@ -406,7 +445,7 @@ class FusedDistributedFNO(nn.Module):
         if "scatter" in st:
             spec: ScatterSpec = st["scatter"]
             if st.get("peer_dst") and self.world > 1:
-                sym = self.sym_S1 if st["dst"] == "S1" else self.sym_T1
+                sym = self.sym_S1 if st["dst"] in ("S1", "S1s") else self.sym_T1
                 ptrs = sym.peer_ptrs()
             else:
                 ptrs = [dst.data_ptr()] * max(self.world, 1)
@@ -425,10 +464,12 @@ class FusedDistributedFNO(nn.Module):
         s3 = self._saved["S3"][block] if (self._train_bufs_ready and not self._eval_mode) else ws["S3w"]
         bufs = {"src": src, "Z1": ws["Z1U"], "S1": ws["S1"], "S2": ws["S2"],
                 "S3": ws["S3w"] if adj else s3, "S4": ws["S4"], "T2": ws["T2"], "T1": ws["T1"],
-                "U": ws["Z1U"], "dst": dst}
+                "U": ws["Z1U"], "dst": dst, "S1s": ws.get("S1s"), "T1s": ws.get("T1s")}
         R = self._seg(f"blocks.{block}.spectral")
         for st in self.chain_desc:
-            if st["name"] == "mix":
+            if st["name"].startswith("perm"):
+                self._C.permute_u32(bufs[st["src"]], bufs[st["dst"]], st["size"], st["sstr"], st["dstr"])
+            elif st["name"] == "mix":
                 if adj:
                     gR = self._seg(f"blocks.{block}.spectral", self.grad_flat)
                     self._C.spectral_mix_bwd(s3, R, bufs["S3"], bufs["S4"], gR, getattr(self, "_acc", False), pl.B, pl.C, pl.Q)

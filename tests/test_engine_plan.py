@@ -32,21 +32,31 @@ def _addresses(spec, M, npairs):
     return peer, off[:, None] + coff[None, :]
 
 
-def _run_chain(plans, ops, src, weights, adj=False):
+def _run_chain(plans, ops, src, weights, adj=False, staged=False):
     """src: list (per rank) of engine-layout arrays; returns list of outputs."""
     P = len(plans)
     pl0 = plans[0]
     bufs = [dict(src=src[r].reshape(-1).copy(),
                  Z1=np.zeros(max(pl0.n_Z1, pl0.n_U)), S1=np.zeros(pl0.n_S1), S2=np.zeros(pl0.n_S2),
                  S3=np.zeros(pl0.n_S3), S4=np.zeros(pl0.n_S3), T2=np.zeros(pl0.n_T2), T1=np.zeros(pl0.n_T1),
+                 S1s=np.full(pl0.n_S1, np.nan), T1s=np.full(pl0.n_T1, np.nan),
                  dst=np.zeros(pl0.n_act)) for r in range(P)]
     for b in bufs:
         b["U"] = b["Z1"]
-    chains = [pl.chain() for pl in plans]
+    chains = [pl.chain(staged=staged) for pl in plans]
     for si in range(len(chains[0])):
         for r in range(P):
             st = chains[r][si]
             pl = plans[r]
+            if st["name"].startswith("perm"):
+                # strided permutation of 32-bit words (= complex pairs): dst walked innermost digit first
+                src_w = bufs[r][st["src"]].reshape(-1, 2)
+                dst_w = bufs[r][st["dst"]].reshape(-1, 2)
+                idx = np.indices(st["size"][::-1]).reshape(len(st["size"]), -1)[::-1]      # digit l of every word
+                so = sum(idx[l] * st["sstr"][l] for l in range(len(st["size"])))
+                do = sum(idx[l] * st["dstr"][l] for l in range(len(st["size"])))
+                dst_w[do] = src_w[so]
+                continue
             if st["name"] == "mix":
                 x = bufs[r]["S3"].reshape(pl.B, pl.C, pl.Q, 2)
                 xc = x[..., 0] + 1j * x[..., 1]
@@ -72,8 +82,8 @@ def _run_chain(plans, ops, src, weights, adj=False):
     return [b["dst"] for b in bufs]
 
 
-@pytest.mark.parametrize("P", [1, 2, 4])
-def test_stage_plan_reproduces_spectral_convolution(P):
+@pytest.mark.parametrize("P,staged", [(1, False), (2, False), (4, False), (2, True), (4, True)])
+def test_stage_plan_reproduces_spectral_convolution(P, staged):
     import dfno_b200 as d
     B, C, X, Y, Z, T = 2, 3, 8, 8, 8, 4
     modes = (2, 2, 2, 3)
@@ -101,7 +111,7 @@ def test_stage_plan_reproduces_spectral_convolution(P):
         src.append(h[:, :, :, pl.y_off:pl.y_off + pl.Yl].reshape(pl.BC, X, pl.Yl, T, Z))
         wn = Wg[:, :, :, :, pl.kz_off:pl.kz_off + pl.kzl, :].permute(0, 1, 4, 5, 3, 2).contiguous()
         weights.append(wn.reshape(C, C, pl.Q).numpy())           # native [i, o, (kzl, mt, KY, KX)]
-    outs = _run_chain(plans, ops, src, weights)
+    outs = _run_chain(plans, ops, src, weights, staged=staged)
     got = np.concatenate([o.reshape(B, C, X, pl.Yl, T, Z) for o, pl in zip(outs, plans)], axis=3)
     got = torch.from_numpy(got).permute(0, 1, 2, 3, 5, 4)
     assert torch.allclose(got, want, atol=1e-10), float((got - want).abs().max())
@@ -111,7 +121,7 @@ def test_stage_plan_reproduces_spectral_convolution(P):
     gh = g.permute(0, 1, 2, 3, 5, 4).contiguous().numpy()
     gsrc = [gh[:, :, :, pl.y_off:pl.y_off + pl.Yl].reshape(pl.BC, X, pl.Yl, T, Z) for pl in plans]
     wadj = [np.conj(np.transpose(w, (1, 0, 2))) for w in weights]
-    gouts = _run_chain(plans, ops, gsrc, wadj, adj=True)
+    gouts = _run_chain(plans, ops, gsrc, wadj, adj=True, staged=staged)
     gx = np.concatenate([o.reshape(B, C, X, pl.Yl, T, Z) for o, pl in zip(gouts, plans)], axis=3)
     lhs = float((got * g).sum())
     rhs = float((torch.from_numpy(gx).permute(0, 1, 2, 3, 5, 4) * x).sum())

@@ -11,7 +11,9 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 CFG = dict(in_shape=[1, 2, 16, 16, 16, 2], nt=8, width=8, modes=(4, 4, 4, 3), blocks=2)
 
 
-def _worker(rank, ws, cfg, use_p2p):
+def _worker(rank, ws, cfg, use_p2p, staged=False):
+    import os
+    os.environ["DFNO_STAGED_SCATTER"] = "1" if staged else "0"
     import dfno_b200 as d
     from dfno_b200.models.fused import FusedAdam, FusedDistributedFNO
     from dfno_b200.parallel.decomposition import shard_bounds, assemble_slices
@@ -24,6 +26,7 @@ def _worker(rank, ws, cfg, use_p2p):
     state = d.gather_global_state(ref, to_all=True)
     net = FusedDistributedFNO(P_x, cfg["in_shape"], cfg["nt"], cfg["width"], cfg["modes"],
                               num_blocks=cfg["blocks"], device=dev, use_p2p=use_p2p)
+    assert net.staged_scatter == staged
     d.load_global_state(net, state, strict=False)
     g = torch.Generator().manual_seed(9)
     xg = torch.randn(*cfg["in_shape"], generator=g).to(dev)
@@ -78,11 +81,12 @@ def _worker(rank, ws, cfg, use_p2p):
     return res
 
 
-@pytest.mark.parametrize("use_p2p", [True, False])
-def test_two_gpu_pencil_matches_reference(use_p2p):
+@pytest.mark.parametrize("use_p2p,staged", [(True, False), (False, False), (True, True)])
+def test_two_gpu_pencil_matches_reference(use_p2p, staged):
+    """``staged``: per-source staging blocks + local permutation instead of direct interleaved peer stores."""
     n = min(torch.cuda.device_count(), 4)
     n = 4 if n >= 4 else 2
-    for r in run_distributed(_worker, n, CFG, use_p2p, cuda=True, timeout=300):
+    for r in run_distributed(_worker, n, CFG, use_p2p, staged, cuda=True, timeout=300):
         assert r["fwd"] < 5e-2 and r["grad"] < 1e-1, r
         assert r.get("loss", 0) < 5e-2, r
         assert r["replica_drift"] == 0.0, r

@@ -189,3 +189,21 @@ def test_adam_kernel_matches_torch():
         pt.grad = gr.clone()
         opt.step()
     assert torch.allclose(p, pt.detach(), atol=2e-6, rtol=1e-5)
+
+
+def test_permute_u32_matches_torch_permute():
+    """Strided 32-bit-word permutation used after the staged pencil transposes."""
+    C = C_()
+    dev = torch.device("cuda")
+    a = torch.randn(3, 4, 5, 6, 2, device=dev).to(torch.bfloat16)          # words = (re, im) bf16 pairs
+    want = a.permute(0, 2, 1, 3, 4).contiguous()
+    out = torch.zeros_like(want)
+    # dst[i0, i2, i1, i3] <- src[i0, i1, i2, i3]; digits innermost first, strides in words
+    C.permute_u32(a.view(-1), out.view(-1), [6, 4, 5, 3], [1, 6 * 5, 6, 6 * 5 * 4], [1, 6, 6 * 4, 6 * 4 * 5])
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    # padded destination pitch: untouched words keep their old content
+    out2 = torch.full((3, 5, 4, 8, 2), 7.0, device=dev, dtype=torch.bfloat16)
+    C.permute_u32(a.view(-1), out2.view(-1), [6, 4, 5, 3], [1, 6 * 5, 6, 6 * 5 * 4], [1, 8, 8 * 4, 8 * 4 * 5])
+    torch.cuda.synchronize()
+    assert torch.equal(out2[..., :6, :], want) and bool((out2[..., 6:, :] == 7.0).all())
