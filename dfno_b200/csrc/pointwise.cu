@@ -342,24 +342,50 @@ __global__ void gelu_probe_kernel(const float* __restrict__ x, float* __restrict
 // Used on the receiving side of the fused pencil transposes: peers deposit their contribution as
 // one long contiguous run per source rank (NVLink-friendly), this kernel interleaves the runs into
 // the K-major layout the next GEMM stage reads.  The tensors are the *truncated* spectra, a few MB.
-struct PermuteDesc { int nd; int size[6]; long long sstr[6]; long long dstr[6]; };
+struct PermuteDesc {
+  int nd;
+  unsigned size[6];
+  unsigned long long magic[6];
+  int shift[6];
+  long long sstr[6];
+  long long dstr[6];
+};
 
+// V = words per thread access (the innermost digit is contiguous on both sides and a multiple of V);
+// digits by magic-number division (n < 2^31); kUnroll independent loads in flight per thread.
+template <typename Vec, int kUnroll>
 __global__ void __launch_bounds__(256)
-permute_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long long total, PermuteDesc d) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long r = i, so = 0, dof = 0;
+permute_vec_kernel(const Vec* __restrict__ src, Vec* __restrict__ dst, unsigned total, PermuteDesc d) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kUnroll) {
+    Vec v[kUnroll];
+    long long dof[kUnroll];
 #pragma unroll
-    for (int l = 0; l < 6; ++l) {
-      if (l < d.nd) {
-        const long long q = r / d.size[l];
-        const long long dig = r - q * d.size[l];
-        r = q;
-        so += dig * d.sstr[l];
-        dof += dig * d.dstr[l];
+    for (int u = 0; u < kUnroll; ++u) {
+      unsigned r = i0 + u * stride;
+      long long so = 0;
+      dof[u] = -1;
+      if (r < total) {
+        dof[u] = 0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+          if (l < d.nd) {
+            unsigned dig = r;
+            if (l != d.nd - 1) {
+              const unsigned q = static_cast<unsigned>((static_cast<unsigned long long>(r) * d.magic[l]) >> d.shift[l]);
+              dig = r - q * d.size[l];
+              r = q;
+            }
+            so += static_cast<long long>(dig) * d.sstr[l];
+            dof[u] += static_cast<long long>(dig) * d.dstr[l];
+          }
+        }
+        v[u] = src[so];
       }
     }
-    dst[dof] = src[so];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (dof[u] >= 0) dst[dof[u]] = v[u];
   }
 }
 
@@ -377,21 +403,46 @@ int grid_for(long long work_items, int threads, int num_sms, int per_sm) {
 const char* permute_u32(const void* src, void* dst, int nd, const int* size, const long long* sstr,
                         const long long* dstr, int num_sms, cudaStream_t s) {
   if (nd < 1 || nd > 6) return "permute_u32: 1..6 digits";
+  // widest vector the innermost (contiguous) digit allows
+  int V = 1;
+  if (sstr[0] == 1 && dstr[0] == 1) {
+    for (int cand = 4; cand > 1 && V == 1; cand >>= 1) {
+      bool ok = size[0] % cand == 0 && reinterpret_cast<uintptr_t>(src) % (4 * cand) == 0 &&
+                reinterpret_cast<uintptr_t>(dst) % (4 * cand) == 0;
+      for (int i = 1; i < nd; ++i) ok = ok && sstr[i] % cand == 0 && dstr[i] % cand == 0;
+      if (ok) V = cand;
+    }
+  }
   PermuteDesc d;
   d.nd = nd;
   long long total = 1;
   for (int i = 0; i < 6; ++i) {
-    d.size[i] = i < nd ? size[i] : 1;
-    d.sstr[i] = i < nd ? sstr[i] : 0;
-    d.dstr[i] = i < nd ? dstr[i] : 0;
-    total *= d.size[i];
+    long long sz = i < nd ? size[i] : 1;
+    if (sz <= 0) return nullptr;
+    if (i == 0) sz /= V;
+    d.size[i] = static_cast<unsigned>(sz);
+    d.sstr[i] = i < nd ? (i == 0 ? sstr[i] : sstr[i] / V) : 0;
+    d.dstr[i] = i < nd ? (i == 0 ? dstr[i] : dstr[i] / V) : 0;
+    int sh = 0;
+    while ((1ull << sh) < static_cast<unsigned long long>(sz)) ++sh;
+    d.magic[i] = ((1ull << (31 + sh)) / static_cast<unsigned long long>(sz)) + 1;
+    d.shift[i] = 31 + sh;
+    total *= sz;
   }
-  if (total <= 0) return nullptr;
-  long long blocks = (total + 255) / 256;
-  const long long cap = static_cast<long long>(num_sms) * 16;
+  if (total >= (1ll << 31)) return "permute_u32: tensor too large for one launch";
+  constexpr int kUnroll = 4;
+  long long blocks = (total + 256 * kUnroll - 1) / (256 * kUnroll);
+  const long long cap = static_cast<long long>(num_sms) * 8;
   if (blocks > cap) blocks = cap;
-  permute_u32_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const uint32_t*>(src),
-                                                              static_cast<uint32_t*>(dst), total, d);
+  const unsigned tot = static_cast<unsigned>(total);
+  const int g = static_cast<int>(blocks);
+  if (V == 4)
+    permute_vec_kernel<uint4, kUnroll><<<g, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), tot, d);
+  else if (V == 2)
+    permute_vec_kernel<uint2, kUnroll><<<g, 256, 0, s>>>(static_cast<const uint2*>(src), static_cast<uint2*>(dst), tot, d);
+  else
+    permute_vec_kernel<uint32_t, kUnroll><<<g, 256, 0, s>>>(static_cast<const uint32_t*>(src),
+                                                            static_cast<uint32_t*>(dst), tot, d);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
