@@ -207,3 +207,24 @@ def test_permute_u32_matches_torch_permute():
     C.permute_u32(a.view(-1), out2.view(-1), [6, 4, 5, 3], [1, 6 * 5, 6, 6 * 5 * 4], [1, 8, 8 * 4, 8 * 4 * 5])
     torch.cuda.synchronize()
     assert torch.equal(out2[..., :6, :], want) and bool((out2[..., 6:, :] == 7.0).all())
+    # 16-byte vector path (inner run of 8 words), 6 digits like the T1 permutation, and an odd inner run (scalar path)
+    for inner in (8, 5):
+        b = torch.randn(2, 3, 2, 4, 3, inner, 2, device=dev).to(torch.bfloat16)
+        wantb = b.permute(0, 4, 2, 1, 3, 5, 6).contiguous()
+        outb = torch.zeros_like(wantb)
+        sz = list(b.shape[:6])                      # src dims [n0..n5], n5 innermost
+        sst = [1] * 6
+        for i in range(4, -1, -1):
+            sst[i] = sst[i + 1] * sz[i + 1]
+        perm = [0, 4, 2, 1, 3, 5]                   # dst dim k is src dim perm[k]
+        dsz = [sz[k] for k in perm]
+        dst_ = [1] * 6
+        for i in range(4, -1, -1):
+            dst_[i] = dst_[i + 1] * dsz[i + 1]
+        # digits innermost first, walking dst
+        size = [dsz[k] for k in range(5, -1, -1)]
+        dstr = [dst_[k] for k in range(5, -1, -1)]
+        sstr = [sst[perm[k]] for k in range(5, -1, -1)]
+        C.permute_u32(b.view(-1), outb.view(-1), size, sstr, dstr)
+        torch.cuda.synchronize()
+        assert torch.equal(outb, wantb), inner
