@@ -40,7 +40,8 @@ static constexpr int kMaxAcc = 8;                  // TMEM accumulator stages
 
 struct SmemLayout {
   uint32_t b_bytes;       // kblocks * n_pad * 128
-  uint32_t a_tile_bytes;  // kblocks * 16384
+  uint32_t a_tile_bytes;  // bytes of one ring stage = kbs * 16384
+  uint32_t kbs;           // 64-wide K blocks per ring stage (= kblocks unless the whole-K tile is too large)
   uint32_t stages;
   uint32_t nacc;          // TMEM accumulator stages (multiple of the number of epilogue groups)
   uint32_t stage_off;     // byte offset of the epilogue staging area
@@ -127,13 +128,16 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int kb = 0; kb < kblocks; ++kb)
         tma_load_2d(smem_b + kb * p.n_pad * 128, &tmB, bfull, kb * kBlockK, 0);
       uint32_t s = 0, ph = 0;
+      const int kbs = static_cast<int>(L.kbs);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], L.a_tile_bytes);
-        uint8_t* dst = smem_a + s * L.a_tile_bytes;
-        for (int kb = 0; kb < kblocks; ++kb)
-          tma_load_2d(dst + kb * (kTileM * 128), &tmA, &full[s], kb * kBlockK, tile * kTileM);
-        if (++s == L.stages) { s = 0; ph ^= 1; }
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kbs) {          // one ring stage per K chunk (usually the whole K)
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], L.a_tile_bytes);
+          uint8_t* dst = smem_a + s * L.a_tile_bytes;
+          for (int kb = 0; kb < kbs; ++kb)
+            tma_load_2d(dst + kb * (kTileM * 128), &tmA, &full[s], (kb0 + kb) * kBlockK, tile * kTileM);
+          if (++s == L.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -142,27 +146,31 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
     mbar_wait(bfull, 0);
     uint32_t s = 0, ph = 0;
+    const int kbs = static_cast<int>(L.kbs);
     int n = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
       const int a = n % nacc;
       mbar_wait(&tempty[a], ((n / nacc) & 1) ^ 1);
-      mbar_wait(&full[s], ph);
-      tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t a_base = smem_u32(smem_a + s * L.a_tile_bytes);
-        const uint32_t b_base = smem_u32(smem_b);
-        const uint32_t d_tmem = tmem_base + a * p.n_pad;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int kb = ks >> 2, kk = ks & 3;
-          const uint64_t adesc = umma_smem_desc_k128(a_base + kb * (kTileM * 128) + kk * 32);
-          const uint64_t bdesc = umma_smem_desc_k128(b_base + kb * (p.n_pad * 128) + kk * 32);
-          umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+      const uint32_t d_tmem = tmem_base + a * p.n_pad;
+      const uint32_t b_base = smem_u32(smem_b);
+      for (int kb0 = 0; kb0 < kblocks; kb0 += kbs) {
+        mbar_wait(&full[s], ph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(smem_a + s * L.a_tile_bytes);
+          const int ks_end = min(ksteps, (kb0 + kbs) * 4);
+          for (int ks = kb0 * 4; ks < ks_end; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            const uint64_t adesc = umma_smem_desc_k128(a_base + (kb - kb0) * (kTileM * 128) + kk * 32);
+            const uint64_t bdesc = umma_smem_desc_k128(b_base + kb * (p.n_pad * 128) + kk * 32);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);             // smem stage may be refilled once the MMAs retire
+          if (kb0 + kbs >= kblocks) umma_commit(&tfull[a]);   // accumulator ready for the epilogue
         }
-        umma_commit(&empty[s]);               // smem stage may be refilled once the MMAs retire
-        umma_commit(&tfull[a]);               // accumulator ready for the epilogue
+        __syncwarp();
+        if (++s == L.stages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == L.stages) { s = 0; ph ^= 1; }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global / peer memory ==========
@@ -405,9 +413,18 @@ const char* dft_gemm_launch(const void* A, long long lda, const void* Bmat, Gemm
   SmemLayout L;
   const int kblocks = p.k_pad / kBlockK;
   L.b_bytes = static_cast<uint32_t>(kblocks) * p.n_pad * 128;
-  L.a_tile_bytes = static_cast<uint32_t>(kblocks) * kTileM * 128;
   const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 4096 /*barriers + tables*/;
-  if (L.b_bytes + 2 * L.a_tile_bytes > budget) return "operator too large for shared memory";
+  // ring stage = the whole-K A tile when two of them fit next to the operator; for long K (up to 512)
+  // the largest divisor of the K blocks that leaves room for >= 3 stages
+  L.kbs = static_cast<uint32_t>(kblocks);
+  if (L.b_bytes + 2u * kblocks * kTileM * 128 > budget) {
+    uint32_t best = 0;
+    for (uint32_t dv = 1; dv < static_cast<uint32_t>(kblocks); ++dv)
+      if (kblocks % dv == 0 && L.b_bytes + 3u * dv * kTileM * 128 <= budget) best = dv;
+    if (!best) return "operator too large for shared memory";
+    L.kbs = best;
+  }
+  L.a_tile_bytes = L.kbs * kTileM * 128;
   // coalesced row-major epilogue: needs N to be a multiple of 8 dividing 256 and aligned rows
   L.stage_off = 0; L.stage_pitch = 0;
   uint32_t stage_total = 0;

@@ -45,6 +45,7 @@ from ..parallel.partition import Partition, create_root_partition
 __all__ = ["FusedDistributedFNO", "FusedAdam", "supports", "wants", "EnginePlan"]
 
 SUPPORTED_WIDTHS = (4, 8, 12, 16, 20, 24, 32)
+MAX_N = 256                  # n_pad limit of dft_gemm (TMEM accumulator columns per stage)
 HEAD_HIDDEN = 128
 
 
@@ -88,10 +89,19 @@ def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width:
         return False, "extents must satisfy Z%8 = T%4 = X%4 = Y%4 = 0 and even modes (TMA pitch alignment)"
     if 2 * mx > X or 2 * my > Y or 2 * mz > Z or mt > T // 2 + 1:
         return False, "mode counts exceed the axes"
-    if max(2 * X, 2 * Y, Z, 2 * T) > 512 or max(2 * X, 2 * Y, Z) > 256 and False:
-        return False, "axis too long for a single resident operator"
-    if max(Z, 2 * T, 2 * X, 2 * Y) > 256:
-        return False, "transformed axes up to 128 complex / 256 real samples are supported"
+    if max(Z, 2 * T) > 256 or max(2 * X, 2 * Y) > 512:
+        return False, "transformed axes: Z <= 256, T <= 128, X, Y <= 256 samples"
+    if B * width * X * (Y // P) * Z * T >= 2 ** 31:
+        return False, "per-rank activation must stay below 2^31 elements"
+    if max(X, Y) > 128:
+        try:                                   # long axes: the inverse stages are issued as column parts
+            pl = EnginePlan(B, Cin, Tin, width, T, X, Y, Z, modes, world=P, rank=0)
+            for staged in {False, P >= 8}:
+                for st in pl.chain(staged=staged):
+                    if "N" in st:
+                        pl.parts(st)
+        except ValueError as e:
+            return False, str(e)
     return True, ""
 
 
@@ -128,6 +138,7 @@ class EnginePlan:
         self.X, self.Y, self.Z = X, Y, Z
         self.mx, self.my, self.mz, self.mt = [int(m) for m in modes]
         self.world, self.rank, self.H = world, rank, hidden
+        self.max_n = MAX_N                                 # widest operator one GEMM launch keeps resident
         self.Yl = Y // world
         self.y_off = rank * self.Yl
         self.KX, self.KY, self.KZ = 2 * self.mx, 2 * self.my, 2 * self.mz
@@ -250,6 +261,27 @@ class EnginePlan:
                        ldc=Z))
         return st
 
+    def parts(self, st: dict) -> List[Tuple[int, int, Optional[ScatterSpec], int, Optional[int]]]:
+        """Column parts of one GEMM stage: ``[(j0, n_pairs, spec, first_peer, n_peers)]``.  A stage
+        whose N fits one resident operator (``max_n``) is a single part; the inverse x / y stages of
+        axes longer than 128 samples (N = 2X, 2Y up to 512) are issued as 2 or 4 launches, each with
+        the operator rows ``[2*j0, 2*(j0+n))`` and the matching slice of the scatter."""
+        npairs = st["N"] // 2
+        if st["N"] <= self.max_n:
+            return [(0, npairs, st.get("scatter"), 0, None)]
+        if "scatter" not in st:
+            raise ValueError(f"stage {st['name']}: row-major output wider than {self.max_n} is not supported")
+        spec: ScatterSpec = st["scatter"]
+        for k in range(2, npairs + 1):
+            if npairs % k or 2 * (npairs // k) > self.max_n:
+                continue
+            n = npairs // k
+            try:
+                return [(j0, n) + spec.column_part(j0, n) for j0 in range(0, npairs, n)]
+            except ValueError:
+                continue
+        raise ValueError(f"stage {st['name']}: no column split of {npairs} pairs fits {self.max_n}")
+
     def operators(self) -> Dict[str, torch.Tensor]:
         """Forward-chain operators (float64) and their adjoint-chain counterparts (``*_adj``)."""
         X, Y, Z, T = self.X, self.Y, self.Z, self.T
@@ -351,7 +383,8 @@ class FusedDistributedFNO(nn.Module):
         self._init_parameters()
 
         # ---- operators (bf16, padded) for the forward and the adjoint chain
-        self.ops = {k: pad_operator(v, device=self.device) for k, v in pl.operators().items()}
+        self._ops_f64 = pl.operators()
+        self.ops = {k: pad_operator(v, device=self.device) for k, v in self._ops_f64.items() if v.shape[0] <= pl.max_n}
 
         # ---- symmetric buffers + barrier
         from ..runtime.symm import PeerBarrier, SymmetricBuffer
@@ -443,20 +476,31 @@ class FusedDistributedFNO(nn.Module):
             self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)
 
     # ------------------------------------------------------------------ kernels
+    def _operator(self, name: str, j0: int, n: int) -> torch.Tensor:
+        """Padded bf16 operator rows ``[2*j0, 2*(j0+n))`` (the whole operator for single-part stages)."""
+        full = self._ops_f64[name]
+        if j0 == 0 and 2 * n == full.shape[0]:
+            return self.ops[name]
+        key = (name, j0, n)
+        if key not in self.ops:
+            self.ops[key] = pad_operator(full[2 * j0:2 * (j0 + n)], device=self.device)
+        return self.ops[key]
+
     def _gemm(self, st: dict, bufs: Dict[str, torch.Tensor], adj: bool, add: Optional[torch.Tensor] = None) -> None:
-        op = self.ops[st["op"] + ("_adj" if adj else "")]
+        name = st["op"] + ("_adj" if adj else "")
         A, dst = bufs[st["src"]], bufs[st["dst"]]
         if "scatter" in st:
-            spec: ScatterSpec = st["scatter"]
             if st.get("peer_dst") and self.world > 1:
                 sym = self.sym_S1 if st["dst"] in ("S1", "S1s") else self.sym_T1
                 ptrs = sym.peer_ptrs()
             else:
                 ptrs = [dst.data_ptr()] * max(self.world, 1)
-            self._C.dft_gemm(A, st["M"], st["K"], st["lda"], op, st["N"], spec.epi(), ptrs, None, 0, 0)
+            for j0, n, spec, p0, pn in self.plan.parts(st):
+                self._C.dft_gemm(A, st["M"], st["K"], st["lda"], self._operator(name, j0, n), 2 * n, spec.epi(),
+                                 ptrs if pn is None else ptrs[p0:p0 + pn], None, 0, 0)
         else:
             epi = [0, 0, st["ldc"], 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 0]
-            self._C.dft_gemm(A, st["M"], st["K"], st["lda"], op, st["N"], epi, [dst.data_ptr()], add,
+            self._C.dft_gemm(A, st["M"], st["K"], st["lda"], self.ops[name], st["N"], epi, [dst.data_ptr()], add,
                              st["ldc"] if add is not None else 0, 0)
         if st.get("barrier_after"):
             self.barrier()

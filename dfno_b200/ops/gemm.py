@@ -63,6 +63,29 @@ class ScatterSpec:
         return [EPI_PAIR_SCATTER, 0, 0, len(self.rows), *R, *SR, J0, 1, SJ0, SJ1, sel, lvl, div,
                 self.base_off]
 
+    def column_part(self, j0: int, n: int) -> Tuple["ScatterSpec", int, Optional[int]]:
+        """The same scatter restricted to pairs ``[j0, j0+n)`` as a stand-alone launch (stages whose
+        N exceeds one resident operator are issued as several column parts).  Returns
+        ``(spec, first_peer, n_peers)``: the part's pair ``j`` lands where pair ``j0+j`` of the full
+        spec does, with the peer table sliced to ``peers[first_peer : first_peer+n_peers]``
+        (``n_peers=None``: unchanged table)."""
+        J0, SJ0, SJ1 = self.cols
+        if self.peer is not None and self.peer[0] == "col":
+            div = self.peer[1]
+            if j0 % div == 0 and n % div == 0:                       # whole peers
+                return ScatterSpec(self.rows, self.cols, self.peer, self.base_off), j0 // div, n // div
+            if div % n == 0 and j0 % n == 0 and J0 % n == 0:         # inside one peer's columns
+                jj = j0 % div
+                off = self.base_off + (jj % J0) * SJ0 + (jj // J0) * SJ1
+                return ScatterSpec(self.rows, (n, SJ0, 0), None, off), j0 // div, 1
+            raise ValueError(f"cannot split {n} pairs at {j0} over peer columns of {div}")
+        if J0 % n == 0 and j0 % n == 0:
+            off = self.base_off + (j0 % J0) * SJ0 + (j0 // J0) * SJ1
+            return ScatterSpec(self.rows, (n, SJ0, 0), self.peer, off), 0, None
+        if n % J0 == 0 and j0 % J0 == 0:
+            return ScatterSpec(self.rows, self.cols, self.peer, self.base_off + (j0 // J0) * SJ1), 0, None
+        raise ValueError(f"cannot split {n} pairs at {j0} with column radix {J0}")
+
     # pure-python model of the addressing, used by the tests and for planning checks
     def address(self, row: int, j: int) -> Tuple[int, int]:
         off, peer, r = self.base_off, 0, row

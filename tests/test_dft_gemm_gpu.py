@@ -23,6 +23,8 @@ def _mk(M, K, N, lda=None, seed=0):
     (2048, 48, 128, 64, True),            # inverse z-DFT, padded pitch
     (129, 20, 40, 24, False),             # inverse t-DFT with padded (kt,ri) pitch
     (70000, 64, 16, None, False),         # many tiles per CTA
+    (128 * 200 + 5, 512, 48, None, False),  # 256-sample complex axis: K chunks stream through the ring
+    (4000, 384, 32, None, True),          # 192-sample axis, chunked (6 K blocks -> 3 per stage)
 ])
 def test_rowmajor_matches_fp32_reference(M, K, N, lda, fp32):
     from dfno_b200.ops.gemm import gemm_rowmajor, pad_operator

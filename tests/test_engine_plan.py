@@ -66,26 +66,34 @@ def _run_chain(plans, ops, src, weights, adj=False, staged=False):
                 continue
             op = ops[st["op"] + ("_adj" if adj else "")].numpy()
             A = bufs[r][st["src"]][: st["M"] * st["lda"]].reshape(st["M"], st["lda"])[:, : st["K"]]
-            Cm = A @ op.T                                       # [M, N]
             if "scatter" in st:
-                peer, off = _addresses(st["scatter"], st["M"], st["N"] // 2)
-                for p in range(P):
-                    sel = peer == p
-                    if not sel.any():
-                        continue
-                    tgt = bufs[p if st.get("peer_dst") else r][st["dst"]]
-                    tgt[off[sel]] = Cm[:, 0::2][sel]
-                    tgt[off[sel] + 1] = Cm[:, 1::2][sel]
-                assert st.get("peer_dst") or (peer == 0).all()
+                for j0, n, spec, p0, pn in pl.parts(st):         # column parts: one launch each on the GPU
+                    Cm = A @ op[2 * j0:2 * (j0 + n)].T           # [M, 2n]
+                    peer, off = _addresses(spec, st["M"], n)
+                    peer = peer + p0
+                    assert pn is None or (peer < p0 + pn).all()
+                    for p in range(P):
+                        sel = peer == p
+                        if not sel.any():
+                            continue
+                        tgt = bufs[p if st.get("peer_dst") else r][st["dst"]]
+                        tgt[off[sel]] = Cm[:, 0::2][sel]
+                        tgt[off[sel] + 1] = Cm[:, 1::2][sel]
+                    assert st.get("peer_dst") or (peer == 0).all()
             else:
+                assert st["N"] <= pl.max_n
+                Cm = A @ op.T                                    # [M, N]
                 bufs[r][st["dst"]][: st["M"] * st["ldc"]].reshape(st["M"], st["ldc"])[:, : st["N"]] = Cm
     return [b["dst"] for b in bufs]
 
 
-@pytest.mark.parametrize("P,staged", [(1, False), (2, False), (4, False), (2, True), (4, True)])
-def test_stage_plan_reproduces_spectral_convolution(P, staged):
+@pytest.mark.parametrize("P,staged,max_n", [(1, False, 256), (2, False, 256), (4, False, 256), (2, True, 256),
+                                             (4, True, 256), (1, False, 8), (2, False, 8), (4, False, 8),
+                                             (4, True, 8), (2, True, 8)])
+def test_stage_plan_reproduces_spectral_convolution(P, staged, max_n):
+    """``max_n`` below the real limit forces the column-part path (used on the GPU for axes > 128)."""
     import dfno_b200 as d
-    B, C, X, Y, Z, T = 2, 3, 8, 8, 8, 4
+    B, C, X, Y, Z, T = 2, 3, 8, (8 if max_n == 256 else 16), 8, 4
     modes = (2, 2, 2, 3)
     torch.manual_seed(0)
     _, P1, _ = d.create_standard_partitions((1, 1, 1, 1, 1, 1))
@@ -103,7 +111,10 @@ def test_stage_plan_reproduces_spectral_convolution(P, staged):
     for r in range(P):
         pl = EnginePlan(B, 1, 1, C, T, X, Y, Z, modes, world=P, rank=r)
         pl.finish(1)
+        pl.max_n = max_n
         plans.append(pl)
+    if max_n != 256:
+        assert sum(len(plans[0].parts(st)) > 1 for st in plans[0].chain(staged=staged) if "N" in st) == 2
     ops = plans[0].operators()
     h = x.permute(0, 1, 2, 3, 5, 4).contiguous().numpy()         # engine layout [B, C, X, Y, T, Z]
     src, weights = [], []

@@ -25,6 +25,7 @@ def _rel(a, b):
 @pytest.mark.parametrize("in_shape,nt,width,modes", [
     ([1, 1, 16, 16, 16, 1], 8, 8, (4, 4, 4, 3)),
     ([2, 2, 12, 8, 24, 3], 12, 20, (2, 4, 6, 7)),
+    ([1, 1, 256, 256, 8, 1], 4, 8, (4, 6, 2, 2)),          # axes > 128: K = 512 stages, column-part inverse stages
 ])
 def test_forward_backward_match_portable_backend(in_shape, nt, width, modes):
     d, ref, fused = _pair(in_shape, nt, width, modes)
