@@ -68,12 +68,19 @@ def _pencil_axis(grid: Sequence[int]) -> Optional[int]:
 
 def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
              modes: Sequence[int]) -> Tuple[bool, str]:
-    """Can the fused engine run this configuration?  Returns ``(ok, reason)``."""
+    """Can the fused engine run this configuration?  Returns ``(ok, reason)``.
+
+    The engine computes on a ``(1,1,1,P,1,1)`` y-pencil.  Any other 6-D ``P_x`` without a batch
+    split (e.g. BASELINE config 3's ``(1,1,2,2,2,1)`` or config 4's 8-way time partition) is served
+    by re-sharding the (small) network input onto that pencil once, running the engine there and
+    re-sharding the single-channel output back -- instead of the reference's two full-resolution
+    re-shards R1/R4 per Fourier layer (``/root/reference/dfno/dfno.py:247,288``)."""
     if P_x.dim != 6:
         return False, "fused engine covers 3-D + time fields (6-D tensors)"
-    if _pencil_axis(P_x.shape) is None:
-        return False, "fused engine needs a (1,1,1,P,1,1) y-pencil partition"
-    P = int(P_x.shape[3])
+    grid = [int(v) for v in P_x.shape]
+    if grid[0] != 1:
+        return False, "batch-partitioned P_x (data parallel) runs on the portable backend"
+    P = int(np.prod(grid))
     B, Cin, X, Y, Z, Tin = [int(s) for s in in_shape]
     T = int(out_timesteps)
     mx, my, mz, mt = [int(m) for m in modes]
@@ -369,6 +376,16 @@ class FusedDistributedFNO(nn.Module):
         self.dtype = torch.bfloat16
         self.block_in_shape = [self.in_shape[0], self.width, *self.in_shape[2:-1], self.out_timesteps]
         B, Cin, X, Y, Z, Tin = self.in_shape
+        # work partition: the y-pencil the engine computes on.  A differently shaped P_x is folded
+        # onto it once at the network's entry / exit (see supports()).
+        self.P_outer, self.P_work = P_x, P_x
+        self.R_in = self.R_out = None
+        if _pencil_axis(P_x.shape) is None:
+            from ..parallel.primitives import Repartition
+            self.P_work = P_x.create_cartesian_topology_partition([1, 1, 1, int(np.prod(P_x.shape)), 1, 1])
+            self.R_in = Repartition(P_x, self.P_work, self.in_shape)
+            self.R_out = Repartition(self.P_work, P_x, [B, 1, X, Y, Z, self.out_timesteps])
+        P_x = self.P_work
         self.world = int(P_x.shape[3]) if P_x.active else 1
         self.rank = int(P_x.index[3]) if P_x.active else 0
         self.plan = EnginePlan(B, Cin, Tin, self.width, self.out_timesteps, X, Y, Z, self.modes,
@@ -442,7 +459,7 @@ class FusedDistributedFNO(nn.Module):
                     t.zero_()
             if self.world > 1:            # replicated pointwise weights: everyone takes rank 0's draw
                 small = self.theta.data[:pl.n_small]
-                dist.broadcast(small, src=self.P_x.world_ranks[0], group=self.P_x.group)
+                dist.broadcast(small, src=self.P_work.world_ranks[0], group=self.P_work.group)
 
     def named_views(self) -> Dict[str, torch.Tensor]:
         return {name: self._seg(name) for name in self.plan.segments}
@@ -661,7 +678,7 @@ class FusedDistributedFNO(nn.Module):
         if self.use_p2p:
             self.allreduce_small_(small)
         else:
-            dist.all_reduce(small, group=self.P_x.group)
+            dist.all_reduce(small, group=self.P_work.group)
 
     def allreduce_small_(self, t: torch.Tensor) -> torch.Tensor:
         """In-place sum of a small contiguous fp32 vector over the pencil through peer memory
@@ -679,7 +696,12 @@ class FusedDistributedFNO(nn.Module):
         return t
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return _FusedFn.apply(x, self.theta, self)
+        if self.R_in is not None:
+            x = self.R_in(x.contiguous())
+        y = _FusedFn.apply(x, self.theta, self)
+        if self.R_out is not None:
+            y = self.R_out(y)
+        return y
 
     # ------------------------------------------------------------------ canonical state <-> engine
     def engine_state_to_global(self, to_all: bool = False):
@@ -701,7 +723,7 @@ class FusedDistributedFNO(nn.Module):
                 mine[key] = tt
         if self.world > 1:
             gathered = [None] * self.world
-            dist.all_gather_object(gathered, mine, group=self.P_x.group)
+            dist.all_gather_object(gathered, mine, group=self.P_work.group)
         else:
             gathered = [mine]
         if not (to_all or self.rank == 0):

@@ -11,14 +11,14 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 CFG = dict(in_shape=[1, 2, 16, 16, 16, 2], nt=8, width=8, modes=(4, 4, 4, 3), blocks=2)
 
 
-def _worker(rank, ws, cfg, use_p2p, staged=False):
+def _worker(rank, ws, cfg, use_p2p, staged=False, grid=None):
     import os
     os.environ["DFNO_STAGED_SCATTER"] = "1" if staged else "0"
     import dfno_b200 as d
     from dfno_b200.models.fused import FusedAdam, FusedDistributedFNO
     from dfno_b200.parallel.decomposition import shard_bounds, assemble_slices
     dev = torch.device("cuda", torch.cuda.current_device())
-    _, P_x, P_0 = d.create_standard_partitions((1, 1, 1, ws, 1, 1))
+    _, P_x, P_0 = d.create_standard_partitions(tuple(grid) if grid else (1, 1, 1, ws, 1, 1))
     P_1 = d.Partition([rank], [1] * 6)
     torch.manual_seed(5)
     ref = d.DistributedFNO(P_1, cfg["in_shape"], cfg["nt"], cfg["width"], cfg["modes"], num_blocks=cfg["blocks"],
@@ -87,6 +87,17 @@ def test_two_gpu_pencil_matches_reference(use_p2p, staged):
     n = min(torch.cuda.device_count(), 4)
     n = 4 if n >= 4 else 2
     for r in run_distributed(_worker, n, CFG, use_p2p, staged, cuda=True, timeout=300):
+        assert r["fwd"] < 5e-2 and r["grad"] < 1e-1, r
+        assert r.get("loss", 0) < 5e-2, r
+        assert r["replica_drift"] == 0.0, r
+
+
+@pytest.mark.parametrize("grid2,grid4", [((1, 1, 2, 1, 1, 1), (1, 1, 2, 1, 2, 1)), ((1, 1, 1, 1, 1, 2), (1, 1, 1, 2, 1, 2))])
+def test_general_partition_is_folded_onto_the_pencil(grid2, grid4):
+    """x/z-split and time-partitioned P_x (BASELINE configs 3 and 4 in miniature): the engine re-shards
+    input and output once and computes on its y-pencil."""
+    n = 4 if torch.cuda.device_count() >= 4 else 2
+    for r in run_distributed(_worker, n, CFG, True, False, grid4 if n == 4 else grid2, cuda=True, timeout=300):
         assert r["fwd"] < 5e-2 and r["grad"] < 1e-1, r
         assert r.get("loss", 0) < 5e-2, r
         assert r["replica_drift"] == 0.0, r
