@@ -65,6 +65,7 @@ def make(name, run_type, mode):
     return [f"./{path.name} {n}" for n in counts]
 
 
+args.out.mkdir(parents=True, exist_ok=True)
 if args.clean_old:
     for f in args.out.glob("*_weak_scaling_*_gpu.sh"):
         f.unlink()

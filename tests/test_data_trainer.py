@@ -77,3 +77,18 @@ def test_trainer_reduces_loss_on_cpu():
     losses = [tr.step(x, y) for _ in range(25)]
     assert losses[-1] < 0.99 * losses[0] and all(b <= a + 1e-3 for a, b in zip(losses, losses[1:]))
     assert abs(tr.evaluate(x, y) - losses[-1]) < 0.1
+
+
+def test_rank_logger_and_metrics_writer(tmp_path, capsys):
+    import json
+    import dfno_b200 as d
+    log = d.get_logger("dfno_b200.test")
+    log.info("hello")
+    d.print0("root line")
+    out = capsys.readouterr().out
+    assert "r0] hello" in out and "root line" in out
+    with d.MetricsWriter(str(tmp_path)) as m:
+        m.log(step=3, loss=torch.tensor(0.5), note="x")
+        m.log(epoch=1, valid_loss=0.25)
+    recs = [json.loads(l) for l in open(tmp_path / "metrics_0000.jsonl")]
+    assert recs[0]["step"] == 3 and recs[0]["loss"] == 0.5 and recs[0]["rank"] == 0 and recs[1]["valid_loss"] == 0.25

@@ -63,6 +63,8 @@ with ctx:
     optimizer = d.FusedAdam(net, lr=args.lr) if fused else (torch.optim.Adam(params, lr=args.lr) if params else None)
     trainer = d.Trainer(net, criterion, optimizer, device=device) if optimizer is not None else None
     start, hist = 0, {"train": [], "valid": []}
+    log = d.get_logger("two_phase")
+    metrics = d.MetricsWriter(args.out_dir)                 # metrics_0000.jsonl on the root
     if args.resume:
         last = d.latest_checkpoint(args.out_dir, max(P_x.rank, 0))
         if last is not None:
@@ -82,15 +84,17 @@ with ctx:
             loss = trainer.step(to_in(x), y.float())
             tot, nbat = tot + loss, nbat + 1
             P_x._comm.Barrier()
-            if P_root.active and j % 50 == 0:
-                print(f"epoch = {epoch}, batch = {j}, loss = {loss:.6f}, dt = {time.time() - t0:.3f}")
+            if j % 50 == 0:
+                log.info(f"epoch = {epoch}, batch = {j}, loss = {loss:.6f}, dt = {time.time() - t0:.3f}")
+                metrics.log(step=epoch * len(train_loader) + j, epoch=epoch, loss=loss, dt=time.time() - t0)
         net.eval()
         vtot, vbat = 0.0, 0
         for x, y in valid_loader:
             vtot, vbat = vtot + trainer.evaluate(to_in(x), y.float()), vbat + 1
         if P_root.active:
             hist["train"].append(tot / max(nbat, 1)); hist["valid"].append(vtot / max(vbat, 1))
-            print(f"epoch = {epoch}, train loss = {hist['train'][-1]:08f}, val loss = {hist['valid'][-1]:08f}")
+            log.info(f"epoch = {epoch}, train loss = {hist['train'][-1]:08f}, val loss = {hist['valid'][-1]:08f}")
+            metrics.log(epoch=epoch, train_loss=hist["train"][-1], valid_loss=hist["valid"][-1])
         if (epoch + 1) % args.checkpoint_interval == 0:
             path = d.save_checkpoint(net, args.out_dir, epoch=epoch + 1, optimizer=optimizer,
                                      extra={"history": hist, "plan": "fused" if fused else "reference"})
@@ -100,6 +104,6 @@ with ctx:
             print(f"rank = {P_x.rank}, saved model: {path}")
     path = d.save_checkpoint(net, args.out_dir, epoch=None, optimizer=optimizer, extra={"history": hist})
     print(f"rank = {P_x.rank}, saved model after final iteration: {path}")
-    if P_root.active:
-        print("training finished.")
+    metrics.close()
+    d.print0("training finished.")
 d.shutdown()
