@@ -42,7 +42,7 @@ from ..ops import operators as OPS
 from ..ops.gemm import ScatterSpec, pad_operator
 from ..parallel.partition import Partition, create_root_partition
 
-__all__ = ["FusedDistributedFNO", "FusedAdam", "supports", "wants", "EnginePlan"]
+__all__ = ["FusedDistributedFNO", "FusedAdam", "supports", "wants", "EnginePlan", "fold_onto_pencil"]
 
 SUPPORTED_WIDTHS = (4, 8, 12, 16, 20, 24, 32)
 MAX_N = 256                  # n_pad limit of dft_gemm (TMEM accumulator columns per stage)
@@ -64,6 +64,17 @@ def _pencil_axis(grid: Sequence[int]) -> Optional[int]:
     if parted == [3]:
         return 3
     return None
+
+
+def fold_onto_pencil(P_x: Partition, in_shape: Sequence[int], out_timesteps: int):
+    """``(P_work, R_in, R_out)``: the y-pencil over ``P_x``'s ranks and the two re-shards that move
+    the network input onto it and the output back (``None`` when ``P_x`` already is that pencil)."""
+    if _pencil_axis(P_x.shape) is not None:
+        return P_x, None, None
+    from ..parallel.primitives import Repartition
+    P_work = P_x.create_cartesian_topology_partition([1, 1, 1, int(np.prod(P_x.shape)), 1, 1])
+    out_shape = [int(in_shape[0]), 1, *[int(v) for v in in_shape[2:-1]], int(out_timesteps)]
+    return P_work, Repartition(P_x, P_work, [int(v) for v in in_shape]), Repartition(P_work, P_x, out_shape)
 
 
 def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
@@ -378,13 +389,8 @@ class FusedDistributedFNO(nn.Module):
         B, Cin, X, Y, Z, Tin = self.in_shape
         # work partition: the y-pencil the engine computes on.  A differently shaped P_x is folded
         # onto it once at the network's entry / exit (see supports()).
-        self.P_outer, self.P_work = P_x, P_x
-        self.R_in = self.R_out = None
-        if _pencil_axis(P_x.shape) is None:
-            from ..parallel.primitives import Repartition
-            self.P_work = P_x.create_cartesian_topology_partition([1, 1, 1, int(np.prod(P_x.shape)), 1, 1])
-            self.R_in = Repartition(P_x, self.P_work, self.in_shape)
-            self.R_out = Repartition(self.P_work, P_x, [B, 1, X, Y, Z, self.out_timesteps])
+        self.P_outer = P_x
+        self.P_work, self.R_in, self.R_out = fold_onto_pencil(P_x, self.in_shape, self.out_timesteps)
         P_x = self.P_work
         self.world = int(P_x.shape[3]) if P_x.active else 1
         self.rank = int(P_x.index[3]) if P_x.active else 0

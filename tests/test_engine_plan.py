@@ -137,3 +137,27 @@ def test_stage_plan_reproduces_spectral_convolution(P, staged, max_n):
     lhs = float((got * g).sum())
     rhs = float((torch.from_numpy(gx).permute(0, 1, 2, 3, 5, 4) * x).sum())
     assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
+class _Grid:
+    """Stand-in for a Partition: ``supports`` only looks at ``dim`` and ``shape``."""
+
+    def __init__(self, *shape):
+        self.shape, self.dim = list(shape), len(shape)
+
+
+def test_supports_covers_the_baseline_configs():
+    from dfno_b200.models.fused import supports
+    # config 2: 128^3 x 20, width 20, 1 x 8 pencil
+    assert supports(_Grid(1, 1, 1, 8, 1, 1), [1, 1, 128, 128, 128, 1], 20, 20, (12, 12, 12, 10))[0]
+    # config 3: 256^3, width 32, 2 x 2 x 2 (folded onto the pencil; axes of 256 samples)
+    assert supports(_Grid(1, 1, 2, 2, 2, 1), [1, 2, 256, 256, 256, 1], 16, 32, (12, 12, 12, 8))[0]
+    # config 4: 64^3 x 32, width 24, 8 modes, 8-way time partition
+    assert supports(_Grid(1, 1, 1, 1, 1, 8), [1, 1, 64, 64, 64, 1], 32, 24, (8, 8, 8, 8))[0]
+    # reference two-phase trainer: 60 x 60 x 64 x 30 on 4 ranks -> T % 4 != 0 -> portable backend
+    ok, why = supports(_Grid(1, 1, 1, 4, 1, 1), [1, 2, 60, 60, 64, 1], 30, 20, (12, 12, 12, 8))
+    assert not ok and "T%4" in why
+    assert not supports(_Grid(2, 1, 1, 4, 1, 1), [2, 1, 64, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]      # data parallel
+    assert not supports(_Grid(1, 1, 1, 16, 1, 1), [1, 1, 64, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]     # > one NVSwitch box
+    assert not supports(_Grid(1, 1, 2, 2, 1), [1, 1, 64, 64, 1], 16, 20, (8, 8, 8))[0]               # 2-D + time
+    assert not supports(_Grid(1, 1, 1, 1, 1, 1), [1, 1, 512, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]     # X > 256

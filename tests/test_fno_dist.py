@@ -148,3 +148,49 @@ def _fnond(rank, ws):
 
 def test_lazy_fnond_and_losses():
     assert all(run_distributed(_fnond, 2))
+
+
+def _fold(rank, ws, grid):
+    """The fused engine's entry/exit fold, with the portable network standing in for the engine:
+    net(P_x) must equal R_out(net(P_work)(R_in(x))) in values and input/parameter gradients."""
+    import dfno_b200 as d
+    from dfno_b200.models.fused import fold_onto_pencil
+    from dfno_b200.parallel.decomposition import shard_bounds, assemble_slices
+    in_shape, nt, width, modes = [1, 2, 8, 8, 8, 2], 4, 3, (2, 2, 2, 2)
+    _, P_x, _ = d.create_standard_partitions(grid)
+    P_work, R_in, R_out = fold_onto_pencil(P_x, in_shape, nt)
+    assert tuple(int(v) for v in P_work.shape) == (1, 1, 1, ws, 1, 1) and R_in is not None
+    torch.manual_seed(3)
+    a = d.DistributedFNO(P_x, in_shape, nt, width, modes, num_blocks=1, dtype=torch.float64, backend="torch")
+    b = d.DistributedFNO(P_work, in_shape, nt, width, modes, num_blocks=1, dtype=torch.float64, backend="torch")
+    d.load_global_state(b, d.gather_global_state(a, to_all=True))
+    g = torch.Generator().manual_seed(1)
+    xg = torch.randn(*in_shape, dtype=torch.float64, generator=g)
+    lo, hi = shard_bounds(in_shape, P_x.shape, P_x.index)
+    xa = xg[assemble_slices(lo, hi)].clone().requires_grad_()
+    xb = xg[assemble_slices(lo, hi)].clone().requires_grad_()
+    ya = a(xa)
+    yb = R_out(b(R_in(xb)))
+    assert ya.shape == yb.shape
+    err = float((ya - yb).abs().max())
+    w = torch.randn(ya.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(7 + rank))
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    gerr = float((xa.grad - xb.grad).abs().max()) if xa.numel() else 0.0
+    ga, gb = d.gather_global_state(_grads(a), to_all=True), d.gather_global_state(_grads(b), to_all=True)
+    perr = max(float((torch.view_as_real(ga[k]) if ga[k].is_complex() else ga[k]).sub(
+        torch.view_as_real(gb[k]) if gb[k].is_complex() else gb[k]).abs().max()) for k in ga if ga[k].numel())
+    return err, gerr, perr
+
+
+def _grads(net):
+    for p in net.parameters():
+        p.data = p.grad if p.grad is not None else torch.zeros_like(p.data)
+    return net
+
+
+@pytest.mark.parametrize("ws,grid", [(2, (1, 1, 2, 1, 1, 1)), (2, (1, 1, 1, 1, 1, 2)), (4, (1, 1, 2, 1, 2, 1)),
+                                     (4, (1, 1, 1, 2, 1, 2))])
+def test_fold_onto_pencil_is_transparent(ws, grid):
+    for err, gerr, perr in run_distributed(_fold, ws, grid):
+        assert err < 1e-10 and gerr < 1e-10 and perr < 1e-10, (err, gerr, perr)
