@@ -103,7 +103,12 @@ def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width:
         return False, "Y and 2*modes_z must divide evenly over the pencil"
     if Cin > 4 or Cin * Tin > 32:
         return False, "lift kernel covers Cin <= 4 and Cin*Tin <= 32"
-    if Z % 8 or T % 4 or Y % 4 or X % 4 or mx % 2 or my % 2 or mz % 2:
+    import os
+    # T % 4 != 0 (e.g. the reference's two-phase run, T = 30) is handled by a padded t pitch in Z1
+    # (EnginePlan.Tp); replayed in float64 by tests/test_engine_plan.py but not yet run on a B200,
+    # hence opt-in for now.
+    t_ok = T % 4 == 0 or (T % 2 == 0 and os.environ.get("DFNO_FUSED_PADDED_T", "0") != "0")
+    if Z % 8 or not t_ok or Y % 4 or X % 4 or mx % 2 or my % 2 or mz % 2:
         return False, "extents must satisfy Z%8 = T%4 = X%4 = Y%4 = 0 and even modes (TMA pitch alignment)"
     if 2 * mx > X or 2 * my > Y or 2 * mz > Z or mt > T // 2 + 1:
         return False, "mode counts exceed the axes"
@@ -163,6 +168,7 @@ class EnginePlan:
         self.kzl = self.KZ // world
         self.kz_off = rank * self.kzl
         self.mtp = (self.mt + 3) // 4 * 4
+        self.Tp = (T + 3) // 4 * 4                         # t pitch of Z1: G1b reads rows of 2*Tp bf16 (16-byte TMA pitch)
         self.BC = B * C
         self.S = X * self.Yl * T * Z                       # positions per (b, c) slab
         self.npos = B * self.S
@@ -171,7 +177,7 @@ class EnginePlan:
         # element counts (bf16 unless noted)
         BC, Yl, kzl, mt, mtp = self.BC, self.Yl, self.kzl, self.mt, self.mtp
         self.n_act = BC * self.S
-        self.n_Z1 = BC * X * self.KZ * Yl * T * 2
+        self.n_Z1 = BC * X * self.KZ * Yl * self.Tp * 2
         self.n_S1 = BC * kzl * mt * X * Y * 2
         self.n_S2 = BC * kzl * mt * self.KY * X * 2
         self.n_S3 = BC * self.Q * 2
@@ -225,20 +231,21 @@ class EnginePlan:
         Yl, KX, KY, KZ, kzl, mt, mtp = self.Yl, self.KX, self.KY, self.KZ, self.kzl, self.mt, self.mtp
         P, r = self.world, self.rank
         m_loc = kzl * mt
+        Tp = self.Tp
         st = []
         if not staged:
             st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
-                           scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * T), (BC * X, KZ * Yl * T * 2)],
-                                               cols=(KZ, Yl * T * 2, 0))))
-            st.append(dict(name="G1b", src="Z1", dst="S1", M=BC * X * KZ * Yl, K=2 * T, lda=2 * T, N=2 * mt, op="G1b",
+                           scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * Tp), (BC * X, KZ * Yl * Tp * 2)],
+                                               cols=(KZ, Yl * Tp * 2, 0))))
+            st.append(dict(name="G1b", src="Z1", dst="S1", M=BC * X * KZ * Yl, K=2 * T, lda=2 * Tp, N=2 * mt, op="G1b",
                            scatter=ScatterSpec(rows=[(Yl, 2), (KZ, mt * X * Y * 2), (X, Y * 2), (BC, m_loc * X * Y * 2)],
                                                cols=(mt, X * Y * 2, 0), peer=("row", 1, kzl), base_off=self.y_off * 2),
                            peer_dst=True, barrier_after=True))
         else:
             st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
-                           scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * T), (X, Yl * 2 * T), (BC, KZ * X * Yl * 2 * T)],
-                                               cols=(KZ, X * Yl * 2 * T, 0))))
-            st.append(dict(name="G1b", src="Z1", dst="S1s", M=BC * KZ * X * Yl, K=2 * T, lda=2 * T, N=2 * mt, op="G1b",
+                           scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * Tp), (X, Yl * 2 * Tp), (BC, KZ * X * Yl * 2 * Tp)],
+                                               cols=(KZ, X * Yl * 2 * Tp, 0))))
+            st.append(dict(name="G1b", src="Z1", dst="S1s", M=BC * KZ * X * Yl, K=2 * T, lda=2 * Tp, N=2 * mt, op="G1b",
                            scatter=ScatterSpec(rows=[(Yl, 2), (X, Yl * 2), (KZ, mt * P * X * Yl * 2),
                                                      (BC, m_loc * P * X * Yl * 2)],
                                                cols=(mt, P * X * Yl * 2, 0), peer=("row", 2, kzl),

@@ -89,12 +89,14 @@ def _run_chain(plans, ops, src, weights, adj=False, staged=False):
 
 @pytest.mark.parametrize("P,staged,max_n", [(1, False, 256), (2, False, 256), (4, False, 256), (2, True, 256),
                                              (4, True, 256), (1, False, 8), (2, False, 8), (4, False, 8),
-                                             (4, True, 8), (2, True, 8)])
+                                             (4, True, 8), (2, True, 8), (1, False, 6), (2, True, 6), (4, False, 6)])
 def test_stage_plan_reproduces_spectral_convolution(P, staged, max_n):
     """``max_n`` below the real limit forces the column-part path (used on the GPU for axes > 128)."""
     import dfno_b200 as d
     B, C, X, Y, Z, T = 2, 3, 8, (8 if max_n == 256 else 16), 8, 4
     modes = (2, 2, 2, 3)
+    if max_n == 6:                      # T = 6 is not a multiple of 4: Z1 carries a padded t pitch (Tp = 8)
+        Y, T, max_n = 8, 6, 256
     torch.manual_seed(0)
     _, P1, _ = d.create_standard_partitions((1, 1, 1, 1, 1, 1))
     blk = d.DistributedFNOBlock(P1, [B, C, X, Y, Z, T], modes, dtype=torch.float64)
