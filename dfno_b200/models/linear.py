@@ -52,6 +52,11 @@ class BroadcastedLinear(nn.Module):
         self.b_bcast = Broadcast(self.P_root, P_x)
         self.W_bcast.link.meta = ((self.out_features, self.in_features), dtype)
         self.b_bcast.link.meta = (tuple(self.b_shape), dtype)
+        # the contraction in einsum notation ("oi,ab..i..->ab..o.."), kept as an attribute for API
+        # parity (/root/reference/dfno/dfno.py:44-49); the forward uses movedim + matmul instead
+        letters = "abcdefghjklmnpqrstuvwxyz"[:P_x.dim]
+        lhs = letters[:self.dim] + "i" + letters[self.dim + 1:]
+        self.eqn = f"oi,{lhs}->{lhs.replace('i', 'o')}"
         self.timer = CommTimer()
         self.dt_comm = 0.0
 
