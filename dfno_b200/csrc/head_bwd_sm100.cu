@@ -223,9 +223,9 @@ head_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int e = 0; e < 2; ++e) {
               const int j = c0 + h2 * 16 + i + e;
               const float pre = __uint_as_float(v[i + e]) + s_b3[j];
-              const GeluParts gp = gelu_parts(pre);
-              const float act = pre * gp.cdf;
-              const float g = dout * s_w4[j] * fmaf(pre, gp.pdf, gp.cdf);
+              const GeluVG gv = gelu_value_grad(pre);
+              const float act = gv.value;
+              const float g = dout * s_w4[j] * gv.grad;
               wsum[h2 * 16 + i + e] = dout * act;       // -> dW4[j]
               gsum[h2 * 16 + i + e] = g;                // -> db3[j]
               g2[e] = g;

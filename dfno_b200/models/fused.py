@@ -30,6 +30,7 @@ Reference call stack being replaced: ``/root/reference/dfno/dfno.py:241-291`` (b
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -103,7 +104,6 @@ def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width:
         return False, "Y and 2*modes_z must divide evenly over the pencil"
     if Cin > 4 or Cin * Tin > 32:
         return False, "lift kernel covers Cin <= 4 and Cin*Tin <= 32"
-    import os
     # T % 4 != 0 (e.g. the reference's two-phase run, T = 30) is handled by a padded t pitch in Z1
     # (EnginePlan.Tp); replayed in float64 by tests/test_engine_plan.py but not yet run on a B200,
     # hence opt-in for now.
@@ -439,19 +439,17 @@ class FusedDistributedFNO(nn.Module):
         }
         self._saved: Dict[str, torch.Tensor] = {}
         self._train_bufs_ready = False
-        import os as _os0
         # staged peer layout (long NVLink runs + local permutation): measured win at 8 GPUs (exposed
         # all-to-all 0.19 -> 0.08 ms per chain), measured loss at 2 (the permutation costs more than the
         # 40-/256-byte runs did); "auto" = on from 8 ranks.
-        _st = _os0.environ.get("DFNO_STAGED_SCATTER", "auto")
+        _st = os.environ.get("DFNO_STAGED_SCATTER", "auto")
         self.staged_scatter = self.world > 1 and (self.world >= 8 if _st == "auto" else _st != "0")
         self.chain_desc = pl.chain(staged=self.staged_scatter)
         if self.staged_scatter:            # peers write the staging blocks; S1 / T1 become local buffers
             self.ws["S1s"], self.ws["T1s"] = self.ws["S1"], self.ws["T1"]
             self.ws["S1"] = torch.empty(pl.n_S1, **bf)
             self.ws["T1"] = torch.zeros(pl.n_T1, **bf)
-        import os as _os
-        self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and _os.environ.get("DFNO_TC_BYPASS", "1") != "0")
+        self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and os.environ.get("DFNO_TC_BYPASS", "1") != "0")
 
     # ------------------------------------------------------------------ parameters
     def _seg(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:

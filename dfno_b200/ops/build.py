@@ -23,6 +23,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xptxas", "-v",
 ]
+# build-time experiments (each changes the source hash, so switching rebuilds):
+#   DFNO_GELU_TANH3=1  tanh-form erf-GELU approximant with one MUFU (csrc/sm100_ptx.cuh)
+if os.environ.get("DFNO_GELU_TANH3", "0") != "0":
+    NVCC_FLAGS.append("-DDFNO_GELU_TANH3")
 
 _lock = threading.Lock()
 _mod = None
