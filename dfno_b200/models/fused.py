@@ -37,11 +37,10 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ..ops import operators as OPS
 from ..ops.gemm import ScatterSpec, pad_operator
-from ..parallel.partition import Partition, create_root_partition
+from ..parallel.partition import Partition
 
 __all__ = ["FusedDistributedFNO", "FusedAdam", "supports", "wants", "EnginePlan", "fold_onto_pencil"]
 

@@ -15,7 +15,6 @@ why it is derived here rather than borrowed from an FFT library.
 from __future__ import annotations
 
 import math
-from typing import Tuple
 
 import torch
 

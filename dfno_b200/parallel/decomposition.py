@@ -12,7 +12,7 @@ Everything here is plain integer math (numpy), usable without torch.distributed.
 from __future__ import annotations
 
 import itertools
-from typing import Dict, Iterable, List, Sequence, Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 import numpy as np
 

@@ -15,7 +15,7 @@ built for one-process-per-GPU on a single NVSwitch box:
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

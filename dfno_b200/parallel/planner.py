@@ -18,11 +18,10 @@ from __future__ import annotations
 
 import itertools
 from dataclasses import dataclass
-from typing import Dict, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 
-from .decomposition import balanced_bounds
 
 __all__ = ["PencilPlan", "make_pencil_plan", "spectrum_shape", "corner_boxes", "validate_modes"]
 

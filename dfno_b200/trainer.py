@@ -7,7 +7,7 @@ computes; the loss value is read back from a pinned scalar.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 

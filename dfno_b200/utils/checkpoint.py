@@ -19,14 +19,14 @@ from __future__ import annotations
 
 import os
 import re
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from ..parallel.decomposition import shard_bounds
-from ..parallel.partition import Partition, world_rank
+from ..parallel.partition import Partition
 
 __all__ = ["gather_global_state", "load_global_state", "save_checkpoint", "load_checkpoint",
            "checkpoint_path", "reshard_checkpoint", "latest_checkpoint",

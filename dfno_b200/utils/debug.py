@@ -16,7 +16,6 @@ from __future__ import annotations
 import os
 import sys
 import threading
-import time
 from typing import Iterable
 
 import torch
