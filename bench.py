@@ -13,6 +13,11 @@ Synthetic fields, random-init weights.
                        all_to_all/broadcast/reduce): the re-expression BASELINE.md describes
 * ``--impl reference`` the unmodified reference from baseline/_ref (needs distdl/mpi4py,
                        which cannot be installed offline -> prints {"unavailable": ...})
+* ``--impl reference-compat``  the unmodified reference *model code* from baseline/_ref (its
+                       DistributedFNO, loss and training loop: fp32, torch.optim.Adam) on the
+                       DistDL/mpi4py import-surface layer in baseline/compat, i.e. with this
+                       repository's NCCL Repartition/Broadcast/SumReduce underneath.  Not the
+                       ``reference`` arm of the task (our communication layer is on its path).
 
 Timing: W warm-up steps, then K steps between CUDA events bracketed by barrier +
 synchronize; max over ranks.  The per-step working set (>= 1.7 GB of activations per block)
@@ -34,13 +39,15 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="fused", choices=["fused", "baseline", "reference"])
+    ap.add_argument("--impl", default="fused", choices=["fused", "baseline", "reference", "reference-compat"])
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--nt", type=int, default=20)
     ap.add_argument("--width", type=int, default=20)
     ap.add_argument("--modes", type=int, nargs=4, default=[12, 12, 12, 10])
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
+                    help="cpu: dry run of the baseline / reference-compat arms on gloo (host-timed; not a benchmark)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -117,11 +124,22 @@ def main():
                    f"offline: {type(e).__name__}: {e}")
         if why is None:
             why = "reference import unexpectedly succeeded but no MPI launcher is available"
-        print(json.dumps({"impl": "reference", "unavailable": why}))
+        print(json.dumps({"impl": "reference", "unavailable": why,
+                          "see_also": "--impl reference-compat (reference model code on baseline/compat)"}))
         return 0
 
-    if args.impl == "baseline":
+    if args.impl in ("baseline", "reference-compat"):
         os.environ["DFNO_P2P_REPARTITION"] = "0"       # stock NCCL all_to_all / broadcast / reduce only
+    ref = None
+    if args.impl == "reference-compat":
+        sys.path[:0] = [os.path.join(ROOT, "baseline", "compat"), os.path.join(ROOT, "baseline", "_ref")]
+        sys.modules.pop("dfno", None)
+        try:
+            import dfno as ref
+            assert os.path.abspath(ref.__file__).startswith(os.path.join(ROOT, "baseline", "_ref"))
+        except Exception as e:       # noqa: BLE001
+            print(json.dumps({"impl": "reference-compat", "unavailable": f"{type(e).__name__}: {e}"}))
+            return 0
     import torch
     import torch.distributed as dist
     import dfno_b200 as d
@@ -136,8 +154,13 @@ def main():
     world = dist.get_world_size() if dist.is_initialized() else 1
     assert world == N, f"world size {world} != --gpus {N}"
     local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    on_gpu = args.device == "cuda"
+    if on_gpu:
+        torch.cuda.set_device(local)
+    elif args.impl == "fused":
+        raise SystemExit("--impl fused needs --device cuda")
+    dev = torch.device("cuda", local) if on_gpu else torch.device("cpu")
+    cdtype = torch.bfloat16 if on_gpu else torch.float32      # compute dtype of the fused / baseline arms
 
     G, T = args.grid, args.nt
     in_shape = [args.batch, 1, G, G, G, 1]
@@ -150,45 +173,79 @@ def main():
                                dtype=torch.bfloat16, backend="fused")
         opt = d.FusedAdam(net, lr=1e-3)
         in_dtype = torch.float32
+    elif ref is not None:
+        # the reference's own objects and its own loop (train_two_phase.py:78-121); fp32 is its dtype
+        _, P_ref, _ = ref.create_standard_partitions(grid)
+        net = ref.DistributedFNO(P_ref, in_shape, T, args.width, list(args.modes), num_blocks=args.blocks,
+                                 device=dev, dtype=torch.float32)
+        params = [p for p in net.parameters() if p.numel() > 0]
+        opt = torch.optim.Adam(params, lr=1e-3) if params else None
+        in_dtype = torch.float32
     else:
         net = d.DistributedFNO(P_x, in_shape, T, args.width, args.modes, num_blocks=args.blocks, device=dev,
-                               dtype=torch.bfloat16, backend="torch")
+                               dtype=cdtype, backend="torch")
         params = [p for p in net.parameters() if p.numel() > 0]
         opt = torch.optim.Adam(params, lr=1e-3)
-        in_dtype = torch.bfloat16
-    crit = d.DistributedRelativeLpLoss(P_x, engine=net if args.impl == "fused" else None)
+        in_dtype = cdtype
+    if ref is not None:
+        crit = ref.DistributedRelativeLpLoss(P_ref).to(dev)
+    else:
+        crit = d.DistributedRelativeLpLoss(P_x, engine=net if args.impl == "fused" else None)
 
     Yl = G // N
-    x_host = torch.randn(args.batch, 1, G, Yl, G, 1, dtype=in_dtype).pin_memory()
-    y_host = torch.randn(args.batch, 1, G, Yl, G, T, dtype=torch.float32).pin_memory()
+    x_host = torch.randn(args.batch, 1, G, Yl, G, 1, dtype=in_dtype)
+    y_host = torch.randn(args.batch, 1, G, Yl, G, T, dtype=torch.float32)
+    if on_gpu:
+        x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     use_graph = args.impl == "fused" and not args.no_graph
-    tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=use_graph)
+    tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=use_graph) if ref is None else None
+
+    def ref_step(xd, yd):
+        if opt is not None:
+            opt.zero_grad()
+        loss = crit(net(xd), yd)
+        loss.backward()
+        if opt is not None:
+            opt.step()
+        return loss
 
     def step_device():
-        return tr.step_on_device(x_dev, y_dev)
+        return tr.step_on_device(x_dev, y_dev) if tr is not None else ref_step(x_dev, y_dev)
+
+    def step_e2e():
+        if tr is not None:
+            return tr.step(x_host, y_host, next_batch=(x_host, y_host))
+        return float(ref_step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)))
 
     def sync_all():
         if N > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if on_gpu:
+            torch.cuda.synchronize()
 
     def timed(fn, steps):
         sync_all()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+        if on_gpu:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+        else:
+            import time
+            t0 = time.perf_counter()
         for _ in range(steps):
             fn()
-        e.record()
+        if on_gpu:
+            e.record()
         sync_all()
-        ms = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+        elapsed = s.elapsed_time(e) if on_gpu else (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([elapsed], device=dev, dtype=torch.float64)
         if N > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and on_gpu:
         sampler.start()                          # covers warm-up + timed region (identical load)
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -204,27 +261,29 @@ def main():
     e2e = None
     if not args.no_e2e:
         for _ in range(3):
-            tr.step(x_host, y_host, next_batch=(x_host, y_host))
-        e2e_ms = timed(lambda: tr.step(x_host, y_host, next_batch=(x_host, y_host)), args.steps)
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
+        nbytes = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
         e2e = {"value": args.batch * 1000.0 / (e2e_ms / args.steps), "unit": "samples/s",
-               "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": tr.h2d_bytes,
-               "d2h_bytes_per_step": tr.d2h_bytes,
-               "cuda_graph": bool(tr._graph is not None),
-               "how": "Trainer.step(): pinned host batch -> async H2D (double buffered) -> fwd+loss+bwd+Adam -> loss D2H"}
+               "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": tr.h2d_bytes if tr is not None else nbytes,
+               "d2h_bytes_per_step": tr.d2h_bytes if tr is not None else 4,
+               "cuda_graph": bool(tr is not None and tr._graph is not None),
+               "how": ("Trainer.step(): pinned host batch -> async H2D (double buffered) -> fwd+loss+bwd+Adam -> loss D2H"
+                       if tr is not None else "reference loop: pinned host batch -> H2D -> fwd+loss+bwd+Adam -> loss.item()")}
 
     if rank == 0:
         out = {
             "metric": "3D Navier-Stokes FNO training step (fwd+loss+bwd+Adam) samples/sec, whole job, device-timed, max over ranks",
             "value": value, "unit": "samples/s", "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic (random fields, random-init weights)", "impl": args.impl,
+            "dtype": "fp32" if (ref is not None or not on_gpu) else "bf16", "data": "synthetic (random fields, random-init weights)", "impl": args.impl,
             "config": {"model": f"FNO3d+t {G}^3x{T}t width {args.width} modes {tuple(args.modes)} blocks {args.blocks}",
                        "global_batch": args.batch, "seq_len": G * G * G * T,
                        "parallelism": f"y-pencil 1x{N} (model parallel: field over y, spectral weights over kz)",
                        "l2": "per-step working set (>=0.2 GB/rank/block activations) exceeds the 126 MB L2; no flush needed",
                        "step": "forward + DistributedRelativeLpLoss + backward + Adam"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "cuda_graph": bool(tr._graph is not None),
+            "cuda_graph": bool(tr is not None and tr._graph is not None),
         }
         print(json.dumps(out))
     if dist.is_initialized():

@@ -75,3 +75,23 @@ def test_reference_style_benchmark_and_generator(tmp_path):
 def test_gradient_check_tool_cli():
     log = _run(["tools/gradient_check.py", "--case", "transpose-linear"])
     assert "passed gradcheck [transpose-linear]" in log and "failed" not in log
+
+
+def test_bench_contract_dry_run():
+    """bench.py on CPU (host-timed dry run): JSON contract keys, the reference arm's `unavailable`
+    line, and the reference-compat arm running the unmodified reference model code."""
+    small = ["--device", "cpu", "--grid", "16", "--nt", "8", "--width", "4", "--modes", "2", "2", "2", "2",
+             "--blocks", "1", "--steps", "2", "--warmup", "3"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True,
+                       text=True, timeout=300, cwd=ROOT)
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    assert r.returncode == 0 and ref["impl"] == "reference" and ("unavailable" in ref or "value" in ref)
+    impls = ["baseline"] + (["reference-compat"] if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "dfno")) else [])
+    for impl in impls:
+        out = _run(["bench.py", "--gpus", "2", "--impl", impl, *small])
+        rec = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                    "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
+            assert key in rec, key
+        assert rec["n_gpus"] == 2 and rec["steps"] == 2 and rec["warmup"] == 3 and rec["impl"] == impl
+        assert "h2d_bytes_per_step" in rec["e2e"] and rec["value"] > 0      # bytes are 0 in the CPU dry run
