@@ -46,6 +46,7 @@ __all__ = ["FusedDistributedFNO", "FusedAdam", "supports", "wants", "EnginePlan"
 
 SUPPORTED_WIDTHS = (4, 8, 12, 16, 20, 24, 32)
 MAX_N = 256                  # n_pad limit of dft_gemm (TMEM accumulator columns per stage)
+HBM_BUDGET = 170 * 2 ** 30   # of a B200's 180 GB: leave room for the CUDA context, NCCL and the allocator
 HEAD_HIDDEN = 128
 
 
@@ -115,9 +116,14 @@ def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width:
         return False, "transformed axes: Z <= 256, T <= 128, X, Y <= 256 samples"
     if B * width * X * (Y // P) * Z * T >= 2 ** 31:
         return False, "per-rank activation must stay below 2^31 elements"
+    pl = EnginePlan(B, Cin, Tin, width, T, X, Y, Z, modes, world=P, rank=0)
+    pl.finish(4)
+    need = pl.memory_bytes(train=True)["total"]
+    if need > HBM_BUDGET:
+        return False, (f"needs {need / 2 ** 30:.0f} GiB per GPU for training with 4 blocks "
+                       f"(budget {HBM_BUDGET / 2 ** 30:.0f} GiB): use more GPUs or a smaller batch")
     if max(X, Y) > 128:
         try:                                   # long axes: the inverse stages are issued as column parts
-            pl = EnginePlan(B, Cin, Tin, width, T, X, Y, Z, modes, world=P, rank=0)
             for staged in {False, P >= 8}:
                 for st in pl.chain(staged=staged):
                     if "N" in st:
@@ -305,6 +311,34 @@ class EnginePlan:
             except ValueError:
                 continue
         raise ValueError(f"stage {st['name']}: no column split of {npairs} pairs fits {self.max_n}")
+
+    def memory_bytes(self, train: bool = True, staged: Optional[bool] = None) -> Dict[str, int]:
+        """Per-rank device memory of the engine for this plan, by category (bytes).  Mirrors the
+        allocations of :class:`FusedDistributedFNO` (``__init__``, ``_ensure_train_buffers``,
+        ``_ensure_eval_buffers``) and :class:`FusedAdam`; used to size shards for the 180 GB of a B200
+        before anything is allocated."""
+        if self.num_blocks is None:
+            raise RuntimeError("call finish(num_blocks) first")
+        if staged is None:
+            staged = self.world >= 8
+        nb, bf, f32 = self.num_blocks, 2, 4
+        cl = self.npos * self.CP                                   # channels-last slab
+        out = {
+            "parameters": self.n_theta * f32,
+            "workspaces": (max(self.n_Z1, self.n_U) + self.n_S1 + self.n_T1 + self.n_S2 + 2 * self.n_S3 + self.n_T2) * bf,
+            "staging": ((self.n_S1 + self.n_T1) * bf if (staged and self.world > 1) else 0)
+                       + (self.n_small * f32 if self.world > 1 else 0),
+            "input_output": self.B * self.S // self.T * self.Cin * self.Tin * f32 + self.B * self.S * f32,
+        }
+        if train:
+            out["saved_activations"] = (2 * nb * self.n_act + nb * self.n_S3 + cl) * bf
+            out["backward_workspaces"] = (2 * self.n_act + cl) * bf
+            out["gradients"] = self.n_theta * f32
+            out["adam_moments"] = 2 * self.n_theta * f32
+        else:
+            out["eval_activations"] = (3 * self.n_act + cl) * bf
+        out["total"] = sum(out.values())
+        return out
 
     def operators(self) -> Dict[str, torch.Tensor]:
         """Forward-chain operators (float64) and their adjoint-chain counterparts (``*_adj``)."""

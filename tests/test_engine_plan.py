@@ -163,3 +163,19 @@ def test_supports_covers_the_baseline_configs():
     assert not supports(_Grid(1, 1, 1, 16, 1, 1), [1, 1, 64, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]     # > one NVSwitch box
     assert not supports(_Grid(1, 1, 2, 2, 1), [1, 1, 64, 64, 1], 16, 20, (8, 8, 8))[0]               # 2-D + time
     assert not supports(_Grid(1, 1, 1, 1, 1, 1), [1, 1, 512, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]     # X > 256
+
+
+def test_memory_plan_sizes_shards_for_a_b200():
+    from dfno_b200.models.fused import HBM_BUDGET, supports
+    pl = EnginePlan(1, 1, 1, 20, 20, 128, 128, 128, (12, 12, 12, 10), world=1, rank=0)
+    pl.finish(4)
+    m = pl.memory_bytes(train=True)
+    act = 20 * 128 ** 3 * 20 * 2                                        # one bf16 activation, 1.68 GB
+    assert m["saved_activations"] >= 8 * act and m["adam_moments"] == 2 * m["parameters"] == 2 * m["gradients"]
+    assert 20 * 2 ** 30 < m["total"] < 40 * 2 ** 30 and m["total"] == sum(v for k, v in m.items() if k != "total")
+    assert pl.memory_bytes(train=False)["total"] < m["total"] / 2
+    # batch 8 of the same field does not fit one GPU; spread over 8 it does
+    ok, why = supports(_Grid(1, 1, 1, 1, 1, 1), [8, 1, 128, 128, 128, 1], 20, 20, (12, 12, 12, 10))
+    assert not ok and ("GiB" in why or "2^31" in why)
+    assert supports(_Grid(1, 1, 1, 8, 1, 1), [8, 1, 128, 128, 128, 1], 20, 20, (12, 12, 12, 10))[0]
+    assert HBM_BUDGET < 180 * 2 ** 30
