@@ -88,3 +88,17 @@ def _repartition(rank, ws, grid_a, grid_b, shape, cplx):
 ])
 def test_repartition_values_and_adjoint(grid_a, grid_b, shape, cplx):
     assert all(run_distributed(_repartition, 4, grid_a, grid_b, shape, cplx))
+
+
+def test_zero_volume_corrector():
+    """Empty result -> scalar 0 with an empty gradient; anything else passes through (E7)."""
+    import dfno_b200 as d
+    e = d.zero_volume_tensor(dtype=torch.float64).requires_grad_()
+    out = d.ZeroVolumeCorrectorFunction.apply(e * 2)
+    assert out.shape == () and float(out) == 0.0
+    out.backward()
+    assert e.grad is not None and e.grad.numel() == 0
+    x = torch.tensor(3.0, dtype=torch.float64, requires_grad=True)
+    y = d.ZeroVolumeCorrectorFunction.apply(x * x)
+    y.backward()
+    assert float(y) == 9.0 and float(x.grad) == 6.0
