@@ -96,14 +96,3 @@ def test_two_gpu_pencil_matches_reference(use_p2p, staged):
         assert r["fwd"] < 5e-2 and r["grad"] < 1e-1, r
         assert r.get("loss", 0) < 5e-2, r
         assert r["replica_drift"] == 0.0, r
-
-
-@pytest.mark.parametrize("grid2,grid4", [((1, 1, 2, 1, 1, 1), (1, 1, 2, 1, 2, 1)), ((1, 1, 1, 1, 1, 2), (1, 1, 1, 2, 1, 2))])
-def test_general_partition_is_folded_onto_the_pencil(grid2, grid4):
-    """x/z-split and time-partitioned P_x (BASELINE configs 3 and 4 in miniature): the engine re-shards
-    input and output once and computes on its y-pencil."""
-    n = _world()
-    for r in run_distributed(_worker, n, CFG, True, False, grid4 if n == 4 else grid2, cuda=True, timeout=300):
-        assert r["fwd"] < 5e-2 and r["grad"] < 1e-1, r
-        assert r.get("loss", 0) < 5e-2, r
-        assert r["replica_drift"] == 0.0, r
