@@ -361,6 +361,25 @@ class EnginePlan:
 # the module
 # =====================================================================================
 
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_RANGE = _NoRange()
+
+
+def _nvtx(name: str):
+    """NVTX range around an engine phase when ``DFNO_NVTX=1`` (for Nsight timelines); free otherwise."""
+    if os.environ.get("DFNO_NVTX", "0") == "0":
+        return _NO_RANGE
+    from ..utils.timers import nvtx_range
+    return nvtx_range(name)
+
+
 class _LaunchCounter:
     """Proxy around the extension module that counts kernel launches issued by the engine
     (reported by ``bench.py`` as ``gpu_launches``)."""
@@ -660,19 +679,23 @@ class FusedDistributedFNO(nn.Module):
             hs = [self.ws["eval_h"][k % 2] for k in range(self.num_blocks)]
             pres = [self.ws["eval_pre"]] * self.num_blocks
         hcl = self._saved["hcl"]
-        C_.lift_fwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
-                    self._seg("linear2.b"), hs[0], self._lift_dims())
+        with _nvtx("dfno.lift"):
+            C_.lift_fwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
+                        self._seg("linear2.b"), hs[0], self._lift_dims())
         for k in range(self.num_blocks):
             last = k == self.num_blocks - 1
-            self._spectral_chain(hs[k], pres[k], k, adj=False)
+            with _nvtx(f"dfno.block{k}.spectral"):
+                self._spectral_chain(hs[k], pres[k], k, adj=False)
             Wb = self._seg(f"blocks.{k}.linear.W")
-            if self.use_tc_bypass:
-                C_.bypass_fwd_tc(hs[k], pres[k], self._wpad(Wb), None if last else hs[k + 1],
-                                 hcl if last else None, pl.CP, pl.B, pl.C, pl.S, save)
-            else:
-                C_.bypass_gelu_fwd(hs[k], pres[k], Wb, None if last else hs[k + 1], hcl if last else None,
-                                   pl.CP, pl.B, pl.C, pl.S, save)
-        return self._head_forward(hcl)
+            with _nvtx(f"dfno.block{k}.bypass_gelu"):
+                if self.use_tc_bypass:
+                    C_.bypass_fwd_tc(hs[k], pres[k], self._wpad(Wb), None if last else hs[k + 1],
+                                     hcl if last else None, pl.CP, pl.B, pl.C, pl.S, save)
+                else:
+                    C_.bypass_gelu_fwd(hs[k], pres[k], Wb, None if last else hs[k + 1], hcl if last else None,
+                                       pl.CP, pl.B, pl.C, pl.S, save)
+        with _nvtx("dfno.head"):
+            return self._head_forward(hcl)
 
     def _backward(self, x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
         pl, C_ = self.plan, self._C
@@ -687,7 +710,8 @@ class FusedDistributedFNO(nn.Module):
             # atomically accumulated segment needs clearing
             self.grad_flat[:pl.n_small].zero_()
         self._acc = bool(self.accumulate_grads and self.theta.grad is self.grad_flat)
-        self._head_backward(hcl, dy.contiguous().float(), gcl)
+        with _nvtx("dfno.head.bwd"):
+            self._head_backward(hcl, dy.contiguous().float(), gcl)
         for k in reversed(range(self.num_blocks)):
             last = k == self.num_blocks - 1
             Wb = self._seg(f"blocks.{k}.linear.W")
@@ -703,7 +727,8 @@ class FusedDistributedFNO(nn.Module):
                 for b in range(pl.B):
                     sl = slice(b * pl.C * pl.S, (b + 1) * pl.C * pl.S)
                     C_.kreduce_gemm(pres[k][sl], pl.S, pl.C, hs[k][sl], pl.S, pl.C, pl.S, gW)
-            self._spectral_chain(pres[k], g, k, adj=True, add=dhb)
+            with _nvtx(f"dfno.block{k}.spectral.bwd"):
+                self._spectral_chain(pres[k], g, k, adj=True, add=dhb)
         C_.lift_bwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
                     self._seg("linear2.b"), g, self._seg("linear1.W", self.grad_flat),
                     self._seg("linear1.b", self.grad_flat), self._seg("linear2.W", self.grad_flat),
