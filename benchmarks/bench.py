@@ -114,7 +114,8 @@ if __name__ == "__main__":
     ap.add_argument("--num-gpus", "-ngpu", type=int, default=0)
     ap.add_argument("--benchmark-type", "-bt", type=str, default="eval", choices=["eval", "grad"])
     ap.add_argument("--output-dir", "-o", type=Path, default=Path("."))
-    ap.add_argument("--backend", type=str, default="auto", choices=["auto", "fused", "torch"])
+    ap.add_argument("--backend", type=str, default=os.environ.get("DFNO_BENCH_BACKEND", "auto"),
+                    choices=["auto", "fused", "torch"])
     ap.add_argument("--dtype", type=str, default="bf16", choices=["bf16", "fp32", "fp64"])
     ap.add_argument("--mydummyargument", nargs="?", required=False)
     a = ap.parse_args()
