@@ -12,6 +12,6 @@ __version__ = "0.1.0"
 from .parallel import *           # noqa: F401,F403
 from .utils import *              # noqa: F401,F403
 from .models import *             # noqa: F401,F403
-from .trainer import Trainer      # noqa: E402,F401
+from .trainer import InferenceSession, Trainer      # noqa: E402,F401
 from .data import *               # noqa: E402,F401,F403
 from .models.fused import FusedDistributedFNO, FusedAdam   # noqa: E402,F401

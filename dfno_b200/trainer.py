@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-__all__ = ["Trainer"]
+__all__ = ["Trainer", "InferenceSession"]
 
 
 class Trainer:
@@ -140,3 +140,98 @@ class Trainer:
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
         return float(self.criterion(self.model(xd), yd))
+
+
+
+class InferenceSession:
+    """Forward-only serving loop: pinned host shard in -> (CUDA-graph replayed) forward -> pinned host
+    shard out.  The counterpart of :class:`Trainer` for deployment; the reference only has the one-shot
+    script ``/root/reference/training/two_phase/test_two_phase.py``.
+
+    ``run`` is synchronous (returns when the output is on the host); ``submit`` / ``result`` split it so
+    that the upload of request ``i+1`` overlaps the forward of request ``i``.  With ``cuda_graph`` the
+    forward of a fixed input shape is captured once and replayed; capture failures fall back to eager
+    launches, as in :class:`Trainer`."""
+
+    def __init__(self, model, device: Optional[torch.device] = None, cuda_graph: bool = True):
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.cuda = self.device.type == "cuda"
+        self.cuda_graph = bool(cuda_graph) and self.cuda
+        self.copy_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._graph = None
+        self._graph_failed = False
+        self._gx = self._gy = None
+        self._out_host = None
+        self._inflight = None
+        self.requests = 0
+        model.eval()
+
+    @torch.no_grad()
+    def _forward(self, xd: torch.Tensor) -> torch.Tensor:
+        if not self.cuda_graph or self._graph_failed:
+            return self.model(xd)
+        if self._graph is None or self._gx.shape != xd.shape or self._gx.dtype != xd.dtype:
+            try:
+                self._gx = torch.empty_like(xd)
+                self._gx.copy_(xd)
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):                 # warm-up (allocations, lazy plans) off-capture
+                    for _ in range(2):
+                        self.model(self._gx)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._gy = self.model(self._gx)
+                self._graph = graph
+            except Exception as e:                            # noqa: BLE001 - capture is an optimisation
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the forward failed ({type(e).__name__}: {e}); running eagerly")
+                self._graph_failed, self._graph = True, None
+                torch.cuda.synchronize(self.device)
+                return self.model(xd)
+        self._gx.copy_(xd, non_blocking=True)
+        self._graph.replay()
+        return self._gy
+
+    def submit(self, x_host: torch.Tensor) -> None:
+        """Enqueue one request: async H2D on the copy stream, forward, async D2H into a pinned buffer."""
+        if self._inflight is not None:
+            raise RuntimeError("collect the previous result() first (one request in flight)")
+        if not self.cuda:
+            with torch.no_grad():
+                self._inflight = (self.model(x_host), None)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            xd = x_host.to(self.device, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(self.copy_stream)
+        cur.wait_event(up)
+        xd.record_stream(cur)
+        y = self._forward(xd)
+        if self._out_host is None or self._out_host.shape != y.shape or self._out_host.dtype != y.dtype:
+            self._out_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        self._out_host.copy_(y, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._inflight = (self._out_host, done)
+
+    def result(self) -> torch.Tensor:
+        """Block until the submitted request is on the host; returns this rank's output shard (a pinned
+        buffer that the next request overwrites -- clone it to keep it)."""
+        if self._inflight is None:
+            raise RuntimeError("nothing submitted")
+        out, done = self._inflight
+        self._inflight = None
+        if done is not None:
+            done.synchronize()
+        self.requests += 1
+        return out
+
+    def run(self, x_host: torch.Tensor) -> torch.Tensor:
+        self.submit(x_host)
+        return self.result()

@@ -3,6 +3,7 @@ import os
 import tempfile
 
 import numpy as np
+import pytest
 import torch
 
 from dfno_b200.utils.testing import run_distributed
@@ -92,3 +93,18 @@ def test_rank_logger_and_metrics_writer(tmp_path, capsys):
         m.log(epoch=1, valid_loss=0.25)
     recs = [json.loads(l) for l in open(tmp_path / "metrics_0000.jsonl")]
     assert recs[0]["step"] == 3 and recs[0]["loss"] == 0.5 and recs[0]["rank"] == 0 and recs[1]["valid_loss"] == 0.25
+
+
+def test_inference_session_cpu():
+    import dfno_b200 as d
+    _, P_x, _ = d.create_standard_partitions((1, 1, 1, 1, 1))
+    net = d.DistributedFNO(P_x, [1, 1, 8, 8, 2], 4, 4, (2, 2, 2), num_blocks=1)
+    sess = d.InferenceSession(net, device=torch.device("cpu"))
+    x = torch.randn(1, 1, 8, 8, 2)
+    y = sess.run(x)
+    with torch.no_grad():
+        assert torch.equal(y, net(x))
+    sess.submit(x)
+    with pytest.raises(RuntimeError):
+        sess.submit(x)
+    assert torch.equal(sess.result(), y) and sess.requests == 2
