@@ -1,0 +1,87 @@
+"""Paths that were written after the last GPU session and are still *opt-in* (off by default, see
+DESIGN.md section 7).  They are exercised here as non-strict xfail: a pass is reported as XPASS and
+means the flag can be dropped; a failure does not turn the suite red because nothing ships on them.
+Every case runs in a spawned child process (``run_distributed`` with one rank) so that a device fault or
+a hang in an unvalidated kernel configuration cannot take the pytest process -- and the tests before it --
+down; the file sorts last for the same reason."""
+import os
+
+import pytest
+import torch
+
+from dfno_b200.utils.testing import run_distributed
+
+pytestmark = pytest.mark.gpu
+experimental = pytest.mark.xfail(strict=False, reason="opt-in path, not yet validated on hardware")
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+
+
+def _padded_t(rank, ws):
+    import dfno_b200 as d
+    from dfno_b200.models.fused import FusedDistributedFNO
+    os.environ["DFNO_FUSED_PADDED_T"] = "1"
+    try:
+        dev = torch.device("cuda", 0)
+        _, P_x, _ = d.create_standard_partitions((1, 1, 1, 1, 1, 1))
+        in_shape, nt, width, modes = [1, 1, 16, 16, 16, 1], 6, 8, (4, 4, 4, 3)
+        torch.manual_seed(0)
+        ref = d.DistributedFNO(P_x, in_shape, nt, width, modes, num_blocks=2, device=dev, dtype=torch.float32,
+                               backend="torch")
+        net = FusedDistributedFNO(P_x, in_shape, nt, width, modes, num_blocks=2, device=dev)
+        d.load_global_state(net, d.gather_global_state(ref, to_all=True), strict=False)
+        x = torch.randn(*in_shape, device=dev)
+        y, y_ref = net(x), ref(x)
+        assert _rel(y, y_ref) < 8e-2, _rel(y, y_ref)
+        t = torch.randn_like(y_ref)
+        ((y - t) ** 2).mean().backward()
+        assert bool(torch.isfinite(net.theta.grad).all())
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("DFNO_FUSED_PADDED_T", None)
+    return True
+
+
+@experimental
+def test_padded_t_pitch_t_not_multiple_of_4():
+    """T = 6 (like the reference's T = 30): Z1 carries a padded t pitch, G1b reads K = 2T of a 2*Tp row."""
+    assert all(run_distributed(_padded_t, 1, cuda=True, timeout=180))
+
+
+def _lean(rank, ws):
+    import dfno_b200 as d
+    dev = torch.device("cuda", 0)
+    _, P_x, _ = d.create_standard_partitions((1, 1, 1, 1, 1, 1))
+    in_shape = [1, 1, 16, 16, 16, 1]
+    torch.manual_seed(0)
+    net = d.DistributedFNO(P_x, in_shape, 8, 8, (4, 4, 4, 3), num_blocks=3, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(*in_shape, device=dev)
+    with torch.no_grad():
+        want = net._forward(x, save=True).clone()
+        got = net._forward(x, save=False)
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-4), float((got - want).abs().max())
+    torch.cuda.synchronize()
+    return True
+
+
+@experimental
+def test_lean_inference_dataflow_matches_training_dataflow():
+    """``_forward(save=False)``: ping-pong activations, no pre-activation write."""
+    assert all(run_distributed(_lean, 1, cuda=True, timeout=180))
+
+
+def _four_rank_worker(rank, ws, grid):
+    from test_fused_multigpu import CFG, _worker
+    return _worker(rank, ws, CFG, True, False, grid)
+
+
+@experimental
+@pytest.mark.multigpu
+@pytest.mark.parametrize("grid", [None, (1, 1, 2, 1, 2, 1), (1, 1, 1, 2, 1, 2)])
+def test_four_rank_pencil_and_folds(grid):
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs >= 4 GPUs")
+    for r in run_distributed(_four_rank_worker, 4, grid, cuda=True, timeout=300):
+        assert r["fwd"] < 5e-2 and r["grad"] < 1e-1 and r["replica_drift"] == 0.0, r
