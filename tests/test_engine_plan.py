@@ -179,3 +179,35 @@ def test_memory_plan_sizes_shards_for_a_b200():
     assert not ok and ("GiB" in why or "2^31" in why)
     assert supports(_Grid(1, 1, 1, 8, 1, 1), [8, 1, 128, 128, 128, 1], 20, 20, (12, 12, 12, 10))[0]
     assert HBM_BUDGET < 180 * 2 ** 30
+
+
+def test_column_parts_address_the_same_elements():
+    """``ScatterSpec.column_part``: pair ``j`` of a part lands exactly where pair ``j0 + j`` of the whole
+    stage does (same peer after slicing the peer table, same element offset), for row-, column- and
+    un-peered specs and for both ways a part can relate to the column radix."""
+    from dfno_b200.ops.gemm import ScatterSpec
+    rng = np.random.default_rng(0)
+    specs = [
+        (ScatterSpec(rows=[(5, 2), (3, 40)], cols=(16, 10, 0), peer=("col", 4), base_off=7), 16),      # 4 peers x 4 cols
+        (ScatterSpec(rows=[(5, 2), (3, 40)], cols=(16, 10, 0), peer=("col", 16), base_off=0), 16),     # one peer
+        (ScatterSpec(rows=[(4, 2), (6, 64), (2, 1000)], cols=(8, 8, 0), peer=("row", 1, 3), base_off=3), 8),
+        (ScatterSpec(rows=[(7, 2)], cols=(4, 14, 200), peer=None, base_off=1), 12),                     # two-level columns
+    ]
+    for spec, npairs in specs:
+        M = int(np.prod([r for r, _ in spec.rows]))
+        for n in (1, 2, 4, 8):
+            if npairs % n:
+                continue
+            try:
+                parts = [(j0, n) + spec.column_part(j0, n) for j0 in range(0, npairs, n)]
+            except ValueError:
+                continue                                   # this split is not expressible; parts() tries the next size
+            for j0, n_, part, p0, pn in parts:
+                for row in rng.integers(0, M, size=6):
+                    for j in range(n_):
+                        peer, off = part.address(int(row), j)
+                        assert (peer + p0, off) == spec.address(int(row), j0 + j), (spec.cols, spec.peer, j0, n_, row, j)
+                        assert pn is None or peer < pn
+    # a split that cannot be expressed is refused, not silently wrong
+    with pytest.raises(ValueError):
+        ScatterSpec(rows=[(4, 2)], cols=(6, 2, 0), peer=("col", 3)).column_part(0, 2)
