@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--modes", type=int, nargs=4, default=[12, 12, 12, 10])
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--in-channels", type=int, default=1)
+    ap.add_argument("--partition", type=int, nargs=6, default=None,
+                    help="P_x (default 1 1 1 GPUS 1 1); other grids run the other BASELINE configs, e.g. "
+                         "--grid 256 --nt 16 --width 32 --modes 12 12 12 8 --in-channels 2 --partition 1 1 2 2 2 1")
     ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
                     help="cpu: dry run of the baseline / reference-compat arms on gloo (host-timed; not a benchmark)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -163,8 +167,10 @@ def main():
     cdtype = torch.bfloat16 if on_gpu else torch.float32      # compute dtype of the fused / baseline arms
 
     G, T = args.grid, args.nt
-    in_shape = [args.batch, 1, G, G, G, 1]
-    grid = (1, 1, 1, N, 1, 1)
+    in_shape = [args.batch, args.in_channels, G, G, G, 1]
+    grid = tuple(args.partition) if args.partition else (1, 1, 1, N, 1, 1)
+    if int(torch.tensor(grid).prod()) != N:
+        raise SystemExit(f"--partition {grid} does not hold --gpus {N} ranks")
     _, P_x, P_0 = d.create_standard_partitions(grid)
     torch.manual_seed(123 + rank)
 
@@ -192,9 +198,10 @@ def main():
     else:
         crit = d.DistributedRelativeLpLoss(P_x, engine=net if args.impl == "fused" else None)
 
-    Yl = G // N
-    x_host = torch.randn(args.batch, 1, G, Yl, G, 1, dtype=in_dtype)
-    y_host = torch.randn(args.batch, 1, G, Yl, G, T, dtype=torch.float32)
+    x_local = [int(v) for v in d.compute_distribution_info(P_x, in_shape)["shape"]]
+    y_local = [int(v) for v in d.compute_distribution_info(P_x, [args.batch, 1, G, G, G, T])["shape"]]
+    x_host = torch.randn(*x_local, dtype=in_dtype)
+    y_host = torch.randn(*y_local, dtype=torch.float32)
     if on_gpu:
         x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
@@ -279,7 +286,8 @@ def main():
             "dtype": "fp32" if (ref is not None or not on_gpu) else "bf16", "data": "synthetic (random fields, random-init weights)", "impl": args.impl,
             "config": {"model": f"FNO3d+t {G}^3x{T}t width {args.width} modes {tuple(args.modes)} blocks {args.blocks}",
                        "global_batch": args.batch, "seq_len": G * G * G * T,
-                       "parallelism": f"y-pencil 1x{N} (model parallel: field over y, spectral weights over kz)",
+                       "parallelism": (f"y-pencil 1x{N} (model parallel: field over y, spectral weights over kz)"
+                                       if not args.partition else f"P_x = {grid} (model parallel domain decomposition)"),
                        "l2": "per-step working set (>=0.2 GB/rank/block activations) exceeds the 126 MB L2; no flush needed",
                        "step": "forward + DistributedRelativeLpLoss + backward + Adam"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
