@@ -16,7 +16,6 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, "..", "csrc"))
-BUILD_DIR = os.path.normpath(os.path.join(_HERE, "..", "_build"))
 NAME = "dfno_b200_C"
 
 NVCC_FLAGS = [
@@ -25,8 +24,12 @@ NVCC_FLAGS = [
 ]
 # build-time experiments (each changes the source hash, so switching rebuilds):
 #   DFNO_GELU_TANH3=1  tanh-form erf-GELU approximant with one MUFU (csrc/sm100_ptx.cuh)
+_VARIANT = ""
 if os.environ.get("DFNO_GELU_TANH3", "0") != "0":
     NVCC_FLAGS.append("-DDFNO_GELU_TANH3")
+    _VARIANT = "_tanh3"
+# every variant has its own in-tree directory, so both can be pre-built on a CPU box and travel together
+BUILD_DIR = os.path.normpath(os.path.join(_HERE, "..", "_build" + _VARIANT))
 
 _lock = threading.Lock()
 _mod = None

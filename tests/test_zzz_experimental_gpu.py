@@ -85,3 +85,42 @@ def test_four_rank_pencil_and_folds(grid):
         pytest.skip("needs >= 4 GPUs")
     for r in run_distributed(_four_rank_worker, 4, grid, cuda=True, timeout=300):
         assert r["fwd"] < 5e-2 and r["grad"] < 1e-1 and r["replica_drift"] == 0.0, r
+
+
+def _tanh3(rank, ws):
+    """Runs in a child whose environment selects the pre-built ``_build_tanh3`` variant."""
+    import dfno_b200 as d
+    from dfno_b200.ops import build
+    assert build.BUILD_DIR.endswith("_build_tanh3") and build.is_built(), "variant not pre-built"
+    x = torch.linspace(-9, 9, 200001, device="cuda")
+    y, dy = build.load().gelu_probe(x)
+    xd = x.double().requires_grad_()
+    ref = torch.nn.functional.gelu(xd)
+    ref.sum().backward()
+    assert float((y.double() - ref.detach()).abs().max()) < 2e-3          # far below bf16 resolution
+    assert float((dy.double() - xd.grad).abs().max()) < 2e-3
+    dev = torch.device("cuda", 0)
+    _, P_x, _ = d.create_standard_partitions((1, 1, 1, 1, 1, 1))
+    in_shape, nt, width, modes = [1, 1, 16, 16, 16, 1], 8, 8, (4, 4, 4, 3)
+    torch.manual_seed(0)
+    ref_net = d.DistributedFNO(P_x, in_shape, nt, width, modes, num_blocks=2, device=dev, dtype=torch.float32,
+                               backend="torch")
+    net = d.FusedDistributedFNO(P_x, in_shape, nt, width, modes, num_blocks=2, device=dev)
+    d.load_global_state(net, d.gather_global_state(ref_net, to_all=True), strict=False)
+    xin = torch.randn(*in_shape, device=dev)
+    assert _rel(net(xin), ref_net(xin)) < 8e-2
+    torch.cuda.synchronize()
+    return True
+
+
+@experimental
+def test_tanh_form_gelu_variant():
+    """``DFNO_GELU_TANH3=1`` build: one MUFU.TANH instead of the 17-instruction A&S erf."""
+    variant = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dfno_b200", "_build_tanh3")
+    if not os.path.isdir(variant):
+        pytest.skip("variant not pre-built (DFNO_GELU_TANH3=1 python -c 'from dfno_b200.ops import build; build.build()')")
+    os.environ["DFNO_GELU_TANH3"] = "1"             # inherited by the spawned child; this process never loads it
+    try:
+        assert all(run_distributed(_tanh3, 1, cuda=True, timeout=240))
+    finally:
+        os.environ.pop("DFNO_GELU_TANH3", None)
