@@ -144,7 +144,10 @@ def wants(args, kwargs, backend: str) -> bool:
         return False
     device = torch.device(cfg.get("device", "cpu"))
     dtype = cfg.get("dtype", torch.float32)
-    ok, why = supports(cfg["P_x"], cfg["in_shape"], cfg["out_timesteps"], cfg["width"], cfg["modes"])
+    try:
+        ok, why = supports(cfg["P_x"], cfg["in_shape"], cfg["out_timesteps"], cfg["width"], cfg["modes"])
+    except Exception as e:           # noqa: BLE001 - malformed arguments: let the portable constructor report them
+        ok, why = False, f"{type(e).__name__}: {e}"
     if backend == "fused":
         if not ok:
             raise ValueError(f"backend='fused' requested but unsupported: {why}")
