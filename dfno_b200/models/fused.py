@@ -343,6 +343,46 @@ class EnginePlan:
         out["total"] = sum(out.values())
         return out
 
+    def cost_model(self, hbm_gbs: float = 6491.8, nvlink_gbs: float = 770.0,
+                   staged: Optional[bool] = None) -> Dict[str, object]:
+        """Bytes every kernel of one training step must move (per rank) and the resulting floors.
+
+        Pure bookkeeping of the dataflow in :class:`FusedDistributedFNO` -- each stage reads its input
+        buffer and writes its output buffer once; nothing is assumed to stay in L2 (the working set of a
+        stage is far above 126 MB for the configurations this is meant for).  ``hbm_gbs`` / ``nvlink_gbs``
+        default to the measured copy bandwidth of ``MEASURED_PEAKS.json`` and the measured peer-copy
+        rate.  Returns ``{"stages": [(name, calls_per_step, hbm_bytes, nvlink_bytes)], "hbm_bytes",
+        "nvlink_bytes", "hbm_floor_ms", "nvlink_ms"}``; the NVLink time is overlappable (the transfers are
+        issued from GEMM epilogues), so the step floor is ``max`` of the two per chain, not their sum."""
+        if self.num_blocks is None:
+            raise RuntimeError("call finish(num_blocks) first")
+        if staged is None:
+            staged = self.world >= 8
+        nb, bf, f32 = self.num_blocks, 2, 4
+        P = self.world
+        act, cl = self.n_act * bf, self.npos * self.CP * bf
+        Z1, S1, S2, S3, T2, U = (self.n_Z1 * bf, self.n_S1 * bf, self.n_S2 * bf, self.n_S3 * bf, self.n_T2 * bf,
+                                 self.n_U * bf)
+        T1 = self.n_T1 // self.mtp * self.mt * bf                      # valid (kt < mt) part
+        W = self.C * self.C * self.Q * 2 * f32                         # one block's spectral shard
+        off = (P - 1) / P if P > 1 else 0.0
+        chain = [("G1a", act + Z1, 0), ("G1b", Z1 + S1, S1 * off), ("G2", S1 + S2, 0), ("G3", S2 + S3, 0),
+                 ("iG3", S3 + T2, 0), ("iG2", T2 + T1, T1 * off), ("iG1b", T1 + U, 0), ("iG1a", U + act, 0)]
+        if staged and P > 1:
+            chain += [("permS1", 2 * S1, 0), ("permT1", 2 * T1, 0)]
+        st = [(n, 2 * nb, b, l) for n, b, l in chain]                  # forward + adjoint chain per block
+        st += [("iG1a add (bwd)", nb, act, 0),
+               ("spectral_mix fwd", nb, 2 * S3 + W, 0), ("spectral_mix bwd", nb, 3 * S3 + 2 * W, 0),
+               ("bypass fwd", nb, 4 * act, 0), ("bypass bwd", nb, 5 * act, 0),
+               ("lift fwd", 1, act, 0), ("lift bwd", 1, act, 0),
+               ("head fwd", 1, cl + self.npos * f32, 0), ("head bwd", 1, 2 * cl + self.npos * f32, 0),
+               ("adam", 1, 7 * self.n_theta * f32, 0)]
+        hbm = sum(c * b for _, c, b, _ in st)
+        link = sum(c * l for _, c, _, l in st)
+        return {"stages": st, "hbm_bytes": hbm, "nvlink_bytes": link,
+                "hbm_floor_ms": hbm / (hbm_gbs * 1e9) * 1e3,
+                "nvlink_ms": link / (nvlink_gbs * 1e9) * 1e3 if link else 0.0}
+
     def operators(self) -> Dict[str, torch.Tensor]:
         """Forward-chain operators (float64) and their adjoint-chain counterparts (``*_adj``)."""
         X, Y, Z, T = self.X, self.Y, self.Z, self.T

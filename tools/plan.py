@@ -53,6 +53,21 @@ def main():
         for k, v in m.items():
             if k != "total" and v:
                 print(f"  {k:22s} {v / 2 ** 30:9.3f} GiB")
+    peaks = {"hbm": 6491.8, "link": 770.0}
+    mp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        try:
+            import json
+            j = json.load(open(mp))
+            peaks["hbm"] = float(j.get("hbm_copy_gbs", j.get("hbm_gbs", peaks["hbm"])))
+        except Exception:       # noqa: BLE001 - fall back to the recorded value
+            pass
+    cm = pl.cost_model(hbm_gbs=peaks["hbm"], nvlink_gbs=peaks["link"])
+    print(f"\ntraffic of one training step per rank: {cm['hbm_bytes'] / 1e9:.2f} GB HBM -> {cm['hbm_floor_ms']:.2f} ms at "
+          f"{peaks['hbm']:.0f} GB/s;  {cm['nvlink_bytes'] / 1e6:.0f} MB over NVLink -> {cm['nvlink_ms']:.3f} ms at "
+          f"{peaks['link']:.0f} GB/s (overlappable)")
+    for name, calls, hb, lb in cm["stages"]:
+        print(f"  {name:18s} x{calls:<3d} {hb / 1e9:8.3f} GB/call" + (f"  + {lb / 1e6:7.1f} MB NVLink" if lb else ""))
     staged = P >= 8
     print(f"\nstage chain ({'staged' if staged else 'direct'} peer layout), one spectral convolution:")
     for st in pl.chain(staged=staged):
