@@ -124,3 +124,38 @@ def test_tanh_form_gelu_variant():
         assert all(run_distributed(_tanh3, 1, cuda=True, timeout=240))
     finally:
         os.environ.pop("DFNO_GELU_TANH3", None)
+
+
+def _tma_box(rank, ws):
+    """Does a 4-D TMA box land in shared memory as the dense K-major tile with the 128-byte swizzle
+    applied to the dense offsets?  (What the permutation-free staged layout would rely on.)"""
+    from dfno_b200.ops import build
+    C = build.load()
+
+    def expect(dense):                              # dense: [128 rows, 64 bf16] K-major tile
+        by = dense.contiguous().view(torch.uint8).reshape(-1).cpu()
+        o = torch.arange(by.numel())
+        p = o ^ (((o >> 7) & 7) << 4)               # SWIZZLE_128B: 16-byte chunk index ^= row index mod 8
+        out = torch.empty_like(by)
+        out[p] = by[o]
+        return out
+
+    res = {}
+    for Yl, box1 in ((16, 2), (32, 1)):             # (32 elems x 2 sources) and (64 elems x 1 source) per row
+        A_, P_, X_ = 2, 4, 128
+        n = A_ * P_ * X_ * Yl * 2
+        src = (torch.arange(n, device="cuda") % 251).to(torch.bfloat16).view(A_, P_, X_, Yl * 2)
+        dims = [Yl * 2, P_, X_, A_]
+        strides = [X_ * Yl * 2, Yl * 2, P_ * X_ * Yl * 2]
+        a, r0 = 1, 2
+        raw = C.tma_probe_4d(src.view(-1), dims, strides, [Yl * 2, box1, 128, 1], [0, r0, 0, a]).cpu()
+        dense = src[a, r0:r0 + box1].permute(1, 0, 2).reshape(128, box1 * Yl * 2)
+        res[f"Yl{Yl}"] = bool(torch.equal(raw, expect(dense)))
+    torch.cuda.synchronize()
+    assert all(res.values()), res
+    return True
+
+
+@experimental
+def test_tma_4d_box_is_a_dense_swizzled_k_major_tile():
+    assert all(run_distributed(_tma_box, 1, cuda=True, timeout=180))
