@@ -128,8 +128,9 @@ def main():
                    f"offline: {type(e).__name__}: {e}")
         if why is None:
             why = "reference import unexpectedly succeeded but no MPI launcher is available"
-        print(json.dumps({"impl": "reference", "unavailable": why,
-                          "see_also": "--impl reference-compat (reference model code on baseline/compat)"}))
+        if int(os.environ.get("RANK", "0")) == 0:          # one line per job, also under torchrun
+            print(json.dumps({"impl": "reference", "unavailable": why,
+                              "see_also": "--impl reference-compat (reference model code on baseline/compat)"}))
         return 0
 
     if args.impl in ("baseline", "reference-compat"):
@@ -142,7 +143,8 @@ def main():
             import dfno as ref
             assert os.path.abspath(ref.__file__).startswith(os.path.join(ROOT, "baseline", "_ref"))
         except Exception as e:       # noqa: BLE001
-            print(json.dumps({"impl": "reference-compat", "unavailable": f"{type(e).__name__}: {e}"}))
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference-compat", "unavailable": f"{type(e).__name__}: {e}"}))
             return 0
     import torch
     import torch.distributed as dist
