@@ -5,6 +5,7 @@ UTMALDG / UTMASTG (TMA tensor load / store), LDTM / STTM (tcgen05.ld / st), UTCB
 SYNCS (mbarrier), MUFU (special function unit), ATOM/RED.
 
     python benchmarks/sass_census.py > profiles/sass_census.txt
+    python benchmarks/sass_census.py --excerpt dft_gemm_kernel > profiles/sass_dft_gemm_excerpt.txt
 """
 import collections
 import os
@@ -18,7 +19,27 @@ COLS = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "U
         "STG/ST", "ATOM/RED"]
 
 
+def excerpt(so: str, kernel: str) -> None:
+    """Only the tcgen05 / TMA / mbarrier / TMEM / global-store instructions of one kernel."""
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    pat = re.compile(r"UTMA|UTC|SYNCS|LDTM|STTM|\bSTG|\bST\.E|FENCE|MEMBAR|ERRBAR")
+    print(f"{kernel} -- tcgen05 / TMA / mbarrier / TMEM-load / global-store instructions "
+          f"(full listing: cuobjdump -sass {os.path.relpath(so)}; python benchmarks/sass_census.py --excerpt {kernel})")
+    keep = False
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            keep = kernel in m.group(1)
+            continue
+        if keep and pat.search(line):
+            print(line.rstrip())
+
+
 def main():
+    default_so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dfno_b200", "_build",
+                              "dfno_b200_C.so")
+    if len(sys.argv) > 2 and sys.argv[1] == "--excerpt":
+        return excerpt(sys.argv[3] if len(sys.argv) > 3 else default_so, sys.argv[2])
     so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                              "dfno_b200", "_build", "dfno_b200_C.so")
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
