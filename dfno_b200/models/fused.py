@@ -230,7 +230,8 @@ class EnginePlan:
         """The GEMM stages of one spectral convolution (forward *or* adjoint: only the operator
         matrices and the end buffers differ).  Strides in bf16 elements.
 
-        ``staged=True`` (multi-GPU) changes how the two pencil transposes cross NVLink: instead of
+        ``staged`` (multi-GPU; ``True``, or ``"r2"`` / ``"r3"`` for one transpose only) changes how the pencil
+        transposes cross NVLink: instead of
         interleaving directly into the consumer layout (64- / 40-byte runs per destination row)
         every source rank deposits its contribution as long contiguous runs into a per-source
         block of a staging buffer (``S1s`` / ``T1s``, >= 512-byte runs), and a tiny local
@@ -240,8 +241,11 @@ class EnginePlan:
         P, r = self.world, self.rank
         m_loc = kzl * mt
         Tp = self.Tp
+        # ``staged``: False / True (both transposes) / "r2" / "r3" (only that transpose through a staging block)
+        staged_r2 = staged is True or staged == "r2"
+        staged_r3 = staged is True or staged == "r3"
         st = []
-        if not staged:
+        if not staged_r2:
             st.append(dict(name="G1a", src="src", dst="Z1", M=BC * X * Yl * T, K=Z, lda=Z, N=2 * KZ, op="G1a",
                            scatter=ScatterSpec(rows=[(T, 2), (Yl, 2 * Tp), (BC * X, KZ * Yl * Tp * 2)],
                                                cols=(KZ, Yl * Tp * 2, 0))))
@@ -270,7 +274,7 @@ class EnginePlan:
         st.append(dict(name="iG3", src="S4", dst="T2", M=BC * m_loc * KY, K=2 * KX, lda=2 * KX, N=2 * X, op="iG3",
                        scatter=ScatterSpec(rows=[(KY, 2), (m_loc, KY * 2), (BC, X * m_loc * KY * 2)],
                                            cols=(X, m_loc * KY * 2, 0))))
-        if not staged:
+        if not staged_r3:
             st.append(dict(name="iG2", src="T2", dst="T1", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
                            scatter=ScatterSpec(rows=[(mt, 2), (kzl, mtp * 2), (X, Yl * KZ * mtp * 2),
                                                      (BC, X * Yl * KZ * mtp * 2)],
@@ -329,8 +333,8 @@ class EnginePlan:
         out = {
             "parameters": self.n_theta * f32,
             "workspaces": (max(self.n_Z1, self.n_U) + self.n_S1 + self.n_T1 + self.n_S2 + 2 * self.n_S3 + self.n_T2) * bf,
-            "staging": ((self.n_S1 + self.n_T1) * bf if (staged and self.world > 1) else 0)
-                       + (self.n_small * f32 if self.world > 1 else 0),
+            "staging": ((self.n_S1 * bf if staged in (True, "r2") else 0) + (self.n_T1 * bf if staged in (True, "r3") else 0)
+                        if self.world > 1 else 0) + (self.n_small * f32 if self.world > 1 else 0),
             "input_output": self.B * self.S // self.T * self.Cin * self.Tin * f32 + self.B * self.S * f32,
         }
         if train:
@@ -368,8 +372,10 @@ class EnginePlan:
         off = (P - 1) / P if P > 1 else 0.0
         chain = [("G1a", act + Z1, 0), ("G1b", Z1 + S1, S1 * off), ("G2", S1 + S2, 0), ("G3", S2 + S3, 0),
                  ("iG3", S3 + T2, 0), ("iG2", T2 + T1, T1 * off), ("iG1b", T1 + U, 0), ("iG1a", U + act, 0)]
-        if staged and P > 1:
-            chain += [("permS1", 2 * S1, 0), ("permT1", 2 * T1, 0)]
+        if P > 1 and staged in (True, "r2"):
+            chain.append(("permS1", 2 * S1, 0))
+        if P > 1 and staged in (True, "r3"):
+            chain.append(("permT1", 2 * T1, 0))
         st = [(n, 2 * nb, b, l) for n, b, l in chain]                  # forward + adjoint chain per block
         st += [("iG1a add (bwd)", nb, act, 0),
                ("spectral_mix fwd", nb, 2 * S3 + W, 0), ("spectral_mix bwd", nb, 3 * S3 + 2 * W, 0),
@@ -537,12 +543,16 @@ class FusedDistributedFNO(nn.Module):
         # staged peer layout (long NVLink runs + local permutation): measured win at 8 GPUs (exposed
         # all-to-all 0.19 -> 0.08 ms per chain), measured loss at 2 (the permutation costs more than the
         # 40-/256-byte runs did); "auto" = on from 8 ranks.
-        _st = os.environ.get("DFNO_STAGED_SCATTER", "auto")
-        self.staged_scatter = self.world > 1 and (self.world >= 8 if _st == "auto" else _st != "0")
+        _st = os.environ.get("DFNO_STAGED_SCATTER", "auto").lower()
+        mode = (self.world >= 8) if _st == "auto" else (_st if _st in ("r2", "r3") else _st != "0")
+        self.staged_scatter = mode if self.world > 1 else False      # False / True / "r2" / "r3"
         self.chain_desc = pl.chain(staged=self.staged_scatter)
-        if self.staged_scatter:            # peers write the staging blocks; S1 / T1 become local buffers
-            self.ws["S1s"], self.ws["T1s"] = self.ws["S1"], self.ws["T1"]
+        # peers write the staging blocks; the consumer-side S1 / T1 become local buffers
+        if self.staged_scatter is True or self.staged_scatter == "r2":
+            self.ws["S1s"] = self.ws["S1"]
             self.ws["S1"] = torch.empty(pl.n_S1, **bf)
+        if self.staged_scatter is True or self.staged_scatter == "r3":
+            self.ws["T1s"] = self.ws["T1"]
             self.ws["T1"] = torch.zeros(pl.n_T1, **bf)
         self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and os.environ.get("DFNO_TC_BYPASS", "1") != "0")
 

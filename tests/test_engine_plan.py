@@ -89,7 +89,8 @@ def _run_chain(plans, ops, src, weights, adj=False, staged=False):
 
 @pytest.mark.parametrize("P,staged,max_n", [(1, False, 256), (2, False, 256), (4, False, 256), (2, True, 256),
                                              (4, True, 256), (1, False, 8), (2, False, 8), (4, False, 8),
-                                             (4, True, 8), (2, True, 8), (1, False, 6), (2, True, 6), (4, False, 6)])
+                                             (4, True, 8), (2, True, 8), (1, False, 6), (2, True, 6), (4, False, 6),
+                                             (4, "r3", 256), (2, "r2", 256), (4, "r2", 8)])
 def test_stage_plan_reproduces_spectral_convolution(P, staged, max_n):
     """``max_n`` below the real limit forces the column-part path (used on the GPU for axes > 128)."""
     import dfno_b200 as d
