@@ -48,7 +48,7 @@ for stage in "$@"; do
     bench1)   run 240 bench_fused_1gpu.json python bench.py --gpus 1 --steps 10 --warmup 3
               run 300 bench_baseline_1gpu.json python bench.py --gpus 1 --steps 4 --warmup 3 --impl baseline ;;
     benchN)   trun "$N"; run 240 "bench_fused_${N}gpu.json" $TR bench.py --gpus "$N" --steps 20 --warmup 5
-              for s in 0 1; do
+              for s in 0 1 r3; do
                 trun "$N"; DFNO_STAGED_SCATTER=$s run 240 "bench_fused_${N}gpu_staged$s.json" $TR bench.py --gpus "$N" --steps 20 --warmup 5 --no-e2e
               done
               trun "$N"; run 300 "bench_baseline_${N}gpu.json" $TR bench.py --gpus "$N" --steps 6 --warmup 3 --impl baseline ;;
