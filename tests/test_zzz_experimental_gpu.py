@@ -97,8 +97,11 @@ def _tanh3(rank, ws):
     xd = x.double().requires_grad_()
     ref = torch.nn.functional.gelu(xd)
     ref.sum().backward()
-    assert float((y.double() - ref.detach()).abs().max()) < 2e-3          # far below bf16 resolution
-    assert float((dy.double() - xd.grad).abs().max()) < 2e-3
+    # error budget relative to bf16 storage (2^-8 of the value): 1e-3 * max(1, |x|) for the value (the MUFU
+    # error of tanh is multiplied by x / 2), 4e-3 absolute for the derivative
+    scale = x.double().abs().clamp_min(1.0)
+    assert float(((y.double() - ref.detach()).abs() / scale).max()) < 1e-3
+    assert float((dy.double() - xd.grad).abs().max()) < 4e-3
     dev = torch.device("cuda", 0)
     _, P_x, _ = d.create_standard_partitions((1, 1, 1, 1, 1, 1))
     in_shape, nt, width, modes = [1, 1, 16, 16, 16, 1], 8, 8, (4, 4, 4, 3)
