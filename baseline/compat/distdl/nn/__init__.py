@@ -1,4 +1,6 @@
-from dfno_b200.models.loss import DistributedMSELoss                       # noqa: F401
-from dfno_b200.models.norm import DistributedBatchNorm                     # noqa: F401
-from dfno_b200.parallel.primitives import (Broadcast, DistributedTranspose,  # noqa: F401
-                                            Repartition, SumReduce)
+"""``distdl.nn`` layers used by slimgroup/dfno, on WORLD-group torch.distributed collectives."""
+from .batchnorm import DistributedBatchNorm                # noqa: F401
+from .broadcast import Broadcast                           # noqa: F401
+from .loss import DistributedMSELoss                       # noqa: F401
+from .repartition import DistributedTranspose, Repartition  # noqa: F401
+from .sum_reduce import SumReduce                          # noqa: F401

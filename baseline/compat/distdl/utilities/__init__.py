@@ -1,1 +1,1 @@
-from . import tensor_decomposition, torch                  # noqa: F401
+from . import slicing, tensor_decomposition, torch        # noqa: F401

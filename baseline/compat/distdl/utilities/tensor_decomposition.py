@@ -1,30 +1,32 @@
-"""Balanced block decomposition helpers with DistDL's names and array conventions
-(used by ``/root/reference/dfno/utils.py:58-70``).  No ``__all__``: the reference relies on
-``np`` arriving through ``from ... import *`` (``utils.py:80``)."""
+"""``distdl.utilities.tensor_decomposition``: balanced block decomposition tables.
+Rule: a length-``n`` axis over ``p`` workers gives the first ``n mod p`` workers ``ceil(n/p)``
+entries and the rest ``floor(n/p)``.  No ``__all__`` on purpose -- the reference's ``utils.py``
+gets ``np`` through ``from ... import *``."""
 import numpy as np
 
-from dfno_b200.parallel.decomposition import assemble_slices, axis_table   # noqa: F401
+from .slicing import _cuts, assemble_slices                # noqa: F401
 
 
 def compute_subtensor_shapes_balanced(tensor_structure, P_shape):
-    """Array of shape ``[*P_shape, ndim]``: the shard shape of every grid position."""
-    shape = [int(s) for s in tensor_structure.shape]
-    grid = [int(p) for p in P_shape]
-    out = np.zeros([*grid, len(shape)], dtype=np.int64)
-    for ax, (n, p) in enumerate(zip(shape, grid)):
-        ext = axis_table(n, p)                              # [p, 2] (start, stop)
-        view = [1] * len(grid)
-        view[ax] = p
-        out[..., ax] = (ext[:, 1] - ext[:, 0]).reshape(view)
-    return out
+    grid = tuple(int(p) for p in P_shape)
+    dims = [int(s) for s in tensor_structure.shape]
+    table = np.zeros(grid + (len(dims),), dtype=int)
+    for pos in np.ndindex(*grid):
+        table[pos] = [np.diff(_cuts(n, p))[i] for n, p, i in zip(dims, grid, pos)]
+    return table
 
 
 def compute_subtensor_start_indices(shapes):
+    grid = shapes.shape[:-1]
     out = np.zeros_like(shapes)
-    for ax in range(shapes.shape[-1]):
-        ext = np.moveaxis(shapes[..., ax], ax, 0)           # extents along the grid axis `ax`
-        starts = np.cumsum(ext, axis=0) - ext
-        out[..., ax] = np.moveaxis(starts, 0, ax)
+    for pos in np.ndindex(*grid):
+        for ax in range(shapes.shape[-1]):
+            before = list(pos)
+            total = 0
+            for i in range(pos[ax]):
+                before[ax] = i
+                total += shapes[tuple(before)][ax]
+            out[pos][ax] = total
     return out
 
 

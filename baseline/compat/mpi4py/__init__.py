@@ -1,2 +1,2 @@
-"""``from mpi4py import MPI`` for the unmodified reference, on torch.distributed (see ../README.md)."""
+"""``from mpi4py import MPI`` for a box without MPI: COMM_WORLD is the default torch.distributed group."""
 from . import MPI                                           # noqa: F401

@@ -115,37 +115,15 @@ class ClockSampler:
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        why = None
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
-            import importlib
-            if "dfno" in sys.modules:
-                del sys.modules["dfno"]
-            importlib.import_module("distdl")
-        except Exception as e:       # noqa: BLE001
-            why = (f"reference needs distdl (git-pinned fork) + mpi4py + an MPI runtime, none installable "
-                   f"offline: {type(e).__name__}: {e}")
-        if why is None:
-            why = "reference import unexpectedly succeeded but no MPI launcher is available"
-        if int(os.environ.get("RANK", "0")) == 0:          # one line per job, also under torchrun
-            print(json.dumps({"impl": "reference", "unavailable": why,
-                              "see_also": "--impl reference-compat (reference model code on baseline/compat)"}))
-        return 0
+    if args.impl in ("reference", "reference-compat"):
+        # the unmodified reference through its own API; nothing of dfno_b200 is imported on this path
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import reference_arm
+        return reference_arm.run(args, ClockSampler)
 
-    if args.impl in ("baseline", "reference-compat"):
+    if args.impl == "baseline":
         os.environ["DFNO_P2P_REPARTITION"] = "0"       # stock NCCL all_to_all / broadcast / reduce only
     ref = None
-    if args.impl == "reference-compat":
-        sys.path[:0] = [os.path.join(ROOT, "baseline", "compat"), os.path.join(ROOT, "baseline", "_ref")]
-        sys.modules.pop("dfno", None)
-        try:
-            import dfno as ref
-            assert os.path.abspath(ref.__file__).startswith(os.path.join(ROOT, "baseline", "_ref"))
-        except Exception as e:       # noqa: BLE001
-            if int(os.environ.get("RANK", "0")) == 0:
-                print(json.dumps({"impl": "reference-compat", "unavailable": f"{type(e).__name__}: {e}"}))
-            return 0
     import torch
     import torch.distributed as dist
     import dfno_b200 as d
