@@ -26,8 +26,8 @@ void check(const char* err, const char* what) {
 void dft_gemm(const at::Tensor& A, int64_t M, int64_t K, int64_t lda, const at::Tensor& Bmat, int64_t N,
               const std::vector<int64_t>& epi, const std::vector<int64_t>& peer_ptrs,
               const c10::optional<at::Tensor>& add_src, int64_t ld_add, int64_t max_ctas,
-              const c10::optional<at::Tensor>& v0, const c10::optional<at::Tensor>& v1, double s0) {
-  TORCH_CHECK(A.is_cuda() && A.scalar_type() == at::kBFloat16, "A must be a CUDA bf16 tensor");
+              const c10::optional<at::Tensor>& v0, const c10::optional<at::Tensor>& v1, double s0, bool a_f16) {
+  TORCH_CHECK(A.is_cuda() && A.scalar_type() == (a_f16 ? at::kHalf : at::kBFloat16), "A must be a CUDA bf16 (or, with a_f16, fp16) tensor");
   TORCH_CHECK(Bmat.is_cuda() && Bmat.scalar_type() == at::kBFloat16 && Bmat.dim() == 2 && Bmat.is_contiguous(),
               "operator must be a contiguous CUDA bf16 [n_pad, k_pad] tensor");
   TORCH_CHECK(epi.size() == 20, "epi descriptor must have 20 entries");
@@ -36,6 +36,7 @@ void dft_gemm(const at::Tensor& A, int64_t M, int64_t K, int64_t lda, const at::
   dfno::GemmParams p{};
   p.M = M; p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.n_pad = static_cast<int>(Bmat.size(0)); p.k_pad = static_cast<int>(Bmat.size(1));
+  p.a_f16 = a_f16 ? 1 : 0;
   auto& e = p.epi;
   e.mode = static_cast<int>(epi[0]); e.out_fp32 = static_cast<int>(epi[1]); e.ldc = epi[2];
   e.nrl = static_cast<int>(epi[3]);
@@ -79,7 +80,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dft_gemm", &dft_gemm, "resident-operator GEMM on tcgen05 (see dft_gemm_sm100.cu)",
         py::arg("A"), py::arg("M"), py::arg("K"), py::arg("lda"), py::arg("Bmat"), py::arg("N"),
         py::arg("epi"), py::arg("peer_ptrs"), py::arg("add_src") = c10::nullopt, py::arg("ld_add") = 0,
-        py::arg("max_ctas") = 0, py::arg("v0") = c10::nullopt, py::arg("v1") = c10::nullopt, py::arg("s0") = 0.0);
+        py::arg("max_ctas") = 0, py::arg("v0") = c10::nullopt, py::arg("v1") = c10::nullopt, py::arg("s0") = 0.0, py::arg("a_f16") = false);
   register_ops(m);
   register_symm(m);
 }

@@ -30,15 +30,9 @@ constexpr int kGroups = 4;
 constexpr uint32_t kColsB = 512;
 constexpr uint32_t kTile = 8192;               // one tensor tile: 2 boxes x 32 rows x 128 B
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void tma_store_commit_and_wait() {
-  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+  tma_store_commit();
+  tma_store_wait_read();
 }
 // byte offset of element (channel c, position t in [0,128)) inside a tile image
 __device__ __forceinline__ uint32_t tile_off(int c, int t) {

@@ -52,6 +52,7 @@ struct GemmParams {
   int K;         // valid reduction length
   int n_pad;     // operator rows in memory   (multiple of 16, <= 256)
   int k_pad;     // operator row length       (multiple of 64)
+  int a_f16;     // A holds IEEE fp16 instead of bf16 (B stays bf16: mixed-format kind::f16 MMA)
   EpiParams epi;
 };
 

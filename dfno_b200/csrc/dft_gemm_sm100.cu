@@ -142,7 +142,8 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad);
+    // a_format lives in bits [7,10): 1 = BF16, 0 = F16
+    const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad) & ~(p.a_f16 ? (7u << 7) : 0u);
     const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
     mbar_wait(bfull, 0);
     uint32_t s = 0, ph = 0;

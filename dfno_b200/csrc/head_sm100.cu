@@ -1,0 +1,589 @@
+// head_sm100.cu -- projection head  out = W4 . gelu(W3 h + b3) + b4  (reference linear3 -> gelu -> linear4,
+// dfno.py:348-351), forward and backward, straight from the engine's CHANNEL-MAJOR activation
+// h[b*C + c][S positions] (no channels-last copy): a tile is 128 consecutive positions of all C channels,
+// dropped into shared memory by TMA as two SWIZZLE_128B boxes of [C rows][64 positions] and used as an
+// MN-major A operand (M = positions, K = channels).  Row C of every tile image is a constant row of ones and
+// column C of the W3 operand holds b3, so the hidden bias rides through the MMA -- and, in the backward, the
+// same ones row turns the tensor core into the reducer for db3 and dW4.  The 128-channel hidden layer never
+// exists in memory.
+//
+//   forward   MMA   pre[pos, j] = sum_c h[c, pos] W3[j, c] + b3[j]
+//             epi   out[pos]    = b4 + sum_j W4[j] gelu(pre[pos, j])      (packed fp16 GELU, HFMA2 dot)
+//
+//   backward  MMA1  pre (as above)
+//             epi A P[pos, j]   = W4[j] gelu'(pre)   ACT[pos, j] = gelu(pre)      (fp16 tiles in smem)
+//                   hs[c, pos]  = s dout[pos] h[c, pos],  hs[C, pos] = s dout[pos]   (fp16, s = 2^k keeps the
+//                                 loss gradient inside the fp16 range; undone when the sums are flushed)
+//             MMA2  dh0[pos, i]    = sum_j P[pos, j] W3[j, i]          epi B: g[i, pos] = dout[pos] dh0[pos, i]
+//             MMA3  D3[j, i]      += sum_pos P[pos, j] hs[i, pos]      -> dW3 (i < C), db3 (i = C)
+//             MMA4  D4[j, i]      += sum_pos ACT[pos, j] hs[i, pos]    -> dW4 (i = C)
+#include "sm100_ptx.cuh"
+#include "kernels.h"
+#include "tma_host.h"
+
+namespace dfno {
+namespace {
+
+constexpr int kHidH = 128;
+constexpr uint32_t kColsHd = 512;
+
+struct RowMap {                      // position row -> element offset in the public [B,1,X,Y,Z,T] layout
+  int nrl;
+  int R[4];
+  long long SR[4];
+  unsigned long long Rm[4];
+  int Rs[4];
+};
+
+__device__ __forceinline__ long long row_to_offset(const RowMap& e, uint32_t r) {
+  long long off = 0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (l < e.nrl) {
+      uint32_t d = r;
+      if (l != e.nrl - 1) {
+        const uint32_t q = static_cast<uint32_t>((static_cast<unsigned long long>(r) * e.Rm[l]) >> e.Rs[l]);
+        d = r - q * static_cast<uint32_t>(e.R[l]);
+        r = q;
+      }
+      off += static_cast<long long>(d) * e.SR[l];
+    }
+  }
+  return off;
+}
+
+void fill_magic(RowMap* m) {
+  for (int l = 0; l < 4; ++l) {
+    const unsigned d = static_cast<unsigned>(m->R[l] > 0 ? m->R[l] : 1);
+    int s = 0;
+    while ((1ull << s) < d) ++s;
+    m->Rm[l] = ((1ull << (31 + s)) / d) + 1;
+    m->Rs[l] = 31 + s;
+  }
+}
+
+// kind::f16 instruction descriptor with fp16 (not bf16) A and B
+__device__ __forceinline__ uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return umma_idesc_bf16_f32(M, N, a_mn, b_mn) & ~((7u << 7) | (7u << 10));
+}
+
+// ================================================================================ forward
+constexpr int kStagesHF = 6;
+constexpr int kGroupsHF = 4;
+constexpr int kThreadsHF = 64 + 128 * kGroupsHF;
+
+struct HeadFwdParams {
+  int B, C, KR;
+  long long S, tiles_per_b;
+  const float* w4b4;          // [128 weights, 1 bias]
+  float* out;
+  RowMap map;
+};
+
+__global__ void __launch_bounds__(kThreadsHF, 1)
+head_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW3,
+                const HeadFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_w3 = smem;                                    // [128 hid][64] K-major, column C = b3
+  uint8_t* s_a = smem + 16384;                             // stages x 2 halves x [KR rows][64 pos]
+  const uint32_t half_bytes = static_cast<uint32_t>(p.KR) * 128;
+  const uint32_t stage_bytes = 2 * half_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + kStagesHF * stage_bytes);
+  uint64_t* full = bars;              // [6]
+  uint64_t* empty = bars + 6;         // [6]
+  uint64_t* tfull = bars + 12;        // [4]
+  uint64_t* tempty = bars + 16;       // [4]
+  uint64_t* wfull = bars + 20;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 21);
+  uint32_t* s_w4 = reinterpret_cast<uint32_t*>(bars + 24);   // [64] fp16x2 pairs of W4 (16-byte aligned)
+  float* s_b4 = reinterpret_cast<float*>(s_w4 + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long num_tiles = p.tiles_per_b * p.B;
+
+  for (uint32_t i = threadIdx.x; i < kStagesHF * stage_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kStagesHF * 2 * 16; i += blockDim.x) {      // the ones row (row C) of every half
+    const uint32_t hb = i >> 4, ch = i & 15;
+    reinterpret_cast<uint2*>(s_a + hb * half_bytes + p.C * 128)[ch] = make_uint2(0x3F803F80u, 0x3F803F80u);
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x)
+    s_w4[i] = h2_bits(h2_from_f32(p.w4b4[2 * i], p.w4b4[2 * i + 1]));
+  if (threadIdx.x == 0) s_b4[0] = p.w4b4[kHidH];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW3);
+    for (int s = 0; s < kStagesHF; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 4; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kColsHd>(tmem_holder);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, 16384);
+      tma_load_2d(s_w3, &tmW3, wfull, 0, 0);
+      uint32_t s = 0, ph = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = static_cast<int>(tile / p.tiles_per_b);
+        const int p0 = static_cast<int>((tile % p.tiles_per_b) * 128);
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], 2u * p.C * 128);
+        uint8_t* st = s_a + s * stage_bytes;
+        tma_load_2d(st, &tmH, &full[s], p0, b * p.C);
+        tma_load_2d(st + half_bytes, &tmH, &full[s], p0 + 64, b * p.C);
+        if (++s == kStagesHF) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16_f32(128, kHidH, /*A MN-major*/ 1, 0);
+    const int ksteps = p.KR >> 4;
+    mbar_wait(wfull, 0);
+    uint32_t s = 0, ph = 0;
+    long long n = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      const int a = static_cast<int>(n & 3);
+      mbar_wait(&tempty[a], ((n >> 2) & 1) ^ 1);
+      mbar_wait(&full[s], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t abase = smem_u32(s_a + s * stage_bytes);
+        const uint32_t wbase = smem_u32(s_w3);
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16_ss(tmem_base + a * 128, umma_smem_desc_mn128(abase + ks * 2048, half_bytes, 1024),
+                       umma_smem_desc_k128(wbase + ks * 32), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+        umma_commit(&tfull[a]);
+      }
+      __syncwarp();
+      if (++s == kStagesHF) { s = 0; ph ^= 1; }
+    }
+  } else {
+    const int q = warp & 3, g = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const float b4 = s_b4[0];
+    long long n = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      if ((n & 3) != g) continue;
+      const int a = static_cast<int>(n & 3);
+      const int b = static_cast<int>(tile / p.tiles_per_b);
+      const long long pos = (tile % p.tiles_per_b) * 128 + m;
+      mbar_wait(&tfull[a], (n >> 2) & 1);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 128;
+      float acc = b4;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + ch * 16, v);
+        tmem_ld_wait();
+        const uint4 wa = reinterpret_cast<const uint4*>(s_w4)[2 * ch], wb = reinterpret_cast<const uint4*>(s_w4)[2 * ch + 1];
+        const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        __half2 part = __float2half2_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          part = __hfma2(gelu_h2(h2_from_f32(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]))),
+                         h2_of_bits(w[i]), part);
+        const float2 f = __half22float2(part);
+        acc += f.x + f.y;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+      if (pos < p.S) p.out[row_to_offset(p.map, static_cast<uint32_t>(b * p.S + pos))] = acc;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kColsHd>(tmem_base);
+}
+
+// ================================================================================ backward
+constexpr int kStagesHB = 3;
+constexpr int kEpiHB = 4;                       // epilogue warps per TMEM lane quarter (one 32-column slice each)
+constexpr int kThreadsHB = 64 + 128 * kEpiHB;
+constexpr uint32_t kHD1 = 0;                    // 2 x 128 : pre-activations
+constexpr uint32_t kHD2 = 256;                  // 2 x 48  : dh tiles
+constexpr uint32_t kHD3 = 352;                  // 48      : dW3 / db3 accumulator [hid lanes, c]
+constexpr uint32_t kHD4 = 400;                  // 48      : dW4 accumulator (column C)
+
+struct HeadBwdParams {
+  int B, C, KR;
+  long long S, tiles_per_b;
+  const float* dout;          // fp32, public layout
+  const float* amax;          // max |dout| (device scalar)
+  const float* W4;
+  __nv_bfloat16* g;           // [B*C, S]
+  float* gW3; float* gb3; float* gW4; float* gb4;
+  RowMap map;
+};
+
+__global__ void __launch_bounds__(kThreadsHB, 1)
+head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW3,
+                 const __grid_constant__ CUtensorMap tmW3T, const HeadBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t half_bytes = static_cast<uint32_t>(p.KR) * 128;
+  const uint32_t tile_bytes = 2 * half_bytes;
+  uint8_t* s_w3 = smem;                                   // 16 KB
+  uint8_t* s_w3t = s_w3 + 16384;                          // 2 k-blocks x [KR c rows][64 hid] fp16
+  uint8_t* s_p = s_w3t + tile_bytes;                      // 2 buffers x 2 x [128 pos][64 hid] fp16
+  uint8_t* s_act = s_p + 65536;
+  uint8_t* s_a = s_act + 65536;                           // stages x h tile
+  uint8_t* s_hs = s_a + kStagesHB * tile_bytes;           // 2 x scaled fp16 copy of the h tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hs + 2 * tile_bytes);
+  uint64_t* a_full = bars;            // [3]
+  uint64_t* a_empty = bars + 3;       // [3]
+  uint64_t* w_full = bars + 6;
+  uint64_t* d1_full = bars + 7;       // [2]
+  uint64_t* d1_empty = bars + 9;      // [2]
+  uint64_t* p_full = bars + 11;       // [2]
+  uint64_t* d2_full = bars + 13;      // [2]
+  uint64_t* all_done = bars + 15;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_dout = reinterpret_cast<float*>(bars + 18);     // [2][128] scaled loss gradient of the tile's rows
+  float* s_gb4 = s_dout + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long num_tiles = p.tiles_per_b * p.B;
+
+  for (uint32_t i = threadIdx.x; i < (kStagesHB + 2) * tile_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kStagesHB * 2 * 16; i += blockDim.x) {
+    const uint32_t hb = i >> 4, ch = i & 15;
+    reinterpret_cast<uint2*>(s_a + hb * half_bytes + p.C * 128)[ch] = make_uint2(0x3F803F80u, 0x3F803F80u);
+  }
+  if (threadIdx.x == 0) s_gb4[0] = 0.f;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW3); tma_prefetch_desc(&tmW3T);
+    for (int s = 0; s < kStagesHB; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 4 * kEpiHB);
+      mbar_init(&p_full[i], 4 * kEpiHB); mbar_init(&d2_full[i], 1);
+    }
+    mbar_init(all_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kColsHd>(tmem_holder);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const float amax = *p.amax;
+  const float scale = amax > 0.f ? exp2f(-ceilf(log2f(amax))) : 1.0f;      // |scale * dout| <= 1
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 16384 + tile_bytes);
+      tma_load_2d(s_w3, &tmW3, w_full, 0, 0);
+      tma_load_2d(s_w3t, &tmW3T, w_full, 0, 0);
+      tma_load_2d(s_w3t + half_bytes, &tmW3T, w_full, 64, 0);
+      uint32_t s = 0, ph = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = static_cast<int>(tile / p.tiles_per_b);
+        const int p0 = static_cast<int>((tile % p.tiles_per_b) * 128);
+        mbar_wait(&a_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&a_full[s], 2u * p.C * 128);
+        uint8_t* st = s_a + s * tile_bytes;
+        tma_load_2d(st, &tmH, &a_full[s], p0, b * p.C);
+        tma_load_2d(st + half_bytes, &tmH, &a_full[s], p0 + 64, b * p.C);
+        if (++s == kStagesHB) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t KR = static_cast<uint32_t>(p.KR);
+    const uint32_t idesc1 = umma_idesc_bf16_f32(128, kHidH, 1, 0);      // pre  = h^T-view . W3^T   (bf16)
+    const uint32_t idesc2 = idesc_f16(128, KR, 0, 0);                   // dh0  = P . W3T^T         (fp16)
+    const uint32_t idesc3 = idesc_f16(128, KR, 1, 0);                   // D3/4 += P^T-view . hs^T  (fp16)
+    const int k1steps = p.KR >> 4;
+    mbar_wait(w_full, 0);
+    uint32_t s = 0, ph = 0;
+    long long n = 0;
+    uint32_t prev_stage = 0;
+    auto part2 = [&](long long mth) {
+      const int pb = static_cast<int>(mth & 1);
+      mbar_wait(&p_full[pb], (mth >> 1) & 1);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t pbase = smem_u32(s_p + pb * 32768);
+        const uint32_t abase = smem_u32(s_act + pb * 32768);
+        const uint32_t hsbase = smem_u32(s_hs + pb * tile_bytes);
+        const uint32_t wtbase = smem_u32(s_w3t);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {            // K = hid
+          const int kb = ks >> 2, kk = ks & 3;
+          umma_bf16_ss(tmem_base + kHD2 + pb * 48, umma_smem_desc_k128(pbase + kb * 16384 + kk * 32),
+                       umma_smem_desc_k128(wtbase + kb * half_bytes + kk * 32), idesc2, ks > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {            // K = positions
+          const int kb = ks >> 2, kk = ks & 3;
+          const uint64_t bdesc = umma_smem_desc_k128(hsbase + kb * half_bytes + kk * 32);
+          umma_bf16_ss(tmem_base + kHD3, umma_smem_desc_mn128(pbase + ks * 2048, 16384, 1024), bdesc, idesc3,
+                       (mth > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16_ss(tmem_base + kHD4, umma_smem_desc_mn128(abase + ks * 2048, 16384, 1024), bdesc, idesc3,
+                       (mth > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&d2_full[pb]);
+        umma_commit(&a_empty[prev_stage]);
+      }
+      __syncwarp();
+    };
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      const int buf = static_cast<int>(n & 1);
+      mbar_wait(&d1_empty[buf], ((n >> 1) & 1) ^ 1);
+      mbar_wait(&a_full[s], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t abase = smem_u32(s_a + s * tile_bytes);
+        const uint32_t wbase = smem_u32(s_w3);
+        for (int ks = 0; ks < k1steps; ++ks)
+          umma_bf16_ss(tmem_base + kHD1 + buf * 128, umma_smem_desc_mn128(abase + ks * 2048, half_bytes, 1024),
+                       umma_smem_desc_k128(wbase + ks * 32), idesc1, ks > 0 ? 1u : 0u);
+        umma_commit(&d1_full[buf]);
+      }
+      __syncwarp();
+      if (n > 0) part2(n - 1);
+      prev_stage = s;
+      if (++s == kStagesHB) { s = 0; ph ^= 1; }
+    }
+    if (n > 0) part2(n - 1);
+    if (lane == 0) umma_commit(all_done);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int e = (warp - 2) >> 2;               // this warp's 32-column slice of the hidden layer
+    const int m = q * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    __half2 w4h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w4h[i] = h2_from_f32(p.W4[32 * e + 2 * i], p.W4[32 * e + 2 * i + 1]);
+    float acc_gb4 = 0.f;
+    long long n = 0;
+    uint32_t s = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      const int buf = static_cast<int>(n & 1), pb = buf;
+      const int b = static_cast<int>(tile / p.tiles_per_b);
+      const long long pos = (tile % p.tiles_per_b) * 128 + m;
+      const bool row_ok = pos < p.S;
+      float dout = 0.f;
+      // the P / ACT / hs buffers were last read by the MMAs of tile n-2
+      if (n >= 2) mbar_wait(&d2_full[pb], ((n >> 1) - 1) & 1);
+      if (e == 0) {
+        if (row_ok) dout = p.dout[row_to_offset(p.map, static_cast<uint32_t>(b * p.S + pos))];
+        acc_gb4 += dout;
+        s_dout[pb * 128 + m] = dout * scale;
+      }
+      mbar_wait(&a_full[s], (n / kStagesHB) & 1);            // TMA image of the h tile visible to this thread
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiHB) : "memory");
+      // ---- hs: scaled fp16 copy of the tile; row C = the scaled loss gradient itself
+      if (tid < (p.C + 1) * 16) {
+        const int row = tid >> 4, j = tid & 15;
+        const uint32_t off = (j >> 3) * half_bytes + row * 128 + (((j & 7) ^ (row & 7)) << 4);
+        const float4 d0 = reinterpret_cast<const float4*>(s_dout + pb * 128 + j * 8)[0];
+        const float4 d1 = reinterpret_cast<const float4*>(s_dout + pb * 128 + j * 8)[1];
+        uint4 hv = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        if (row < p.C) hv = *reinterpret_cast<const uint4*>(s_a + s * tile_bytes + off);
+        float2 f;
+        uint4 o;
+        f = unpack_bf16x2(hv.x); o.x = h2_bits(h2_from_f32(f.x * d0.x, f.y * d0.y));
+        f = unpack_bf16x2(hv.y); o.y = h2_bits(h2_from_f32(f.x * d0.z, f.y * d0.w));
+        f = unpack_bf16x2(hv.z); o.z = h2_bits(h2_from_f32(f.x * d1.x, f.y * d1.y));
+        f = unpack_bf16x2(hv.w); o.w = h2_bits(h2_from_f32(f.x * d1.z, f.y * d1.w));
+        *reinterpret_cast<uint4*>(s_hs + pb * tile_bytes + off) = o;
+      }
+      mbar_wait(&d1_full[buf], (n >> 1) & 1);
+      tcgen05_fence_after();
+      {
+        const uint32_t t1 = tmem_base + lane_addr + kHD1 + buf * 128 + 32 * e;
+        uint8_t* prow = s_p + pb * 32768 + ((32 * e) >> 6) * 16384 + m * 128;
+        uint8_t* arow = s_act + pb * 32768 + ((32 * e) >> 6) * 16384 + m * 128;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t1 + h2 * 16, v);
+          tmem_ld_wait();
+          uint32_t pw[8], aw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const GeluH2 vg = gelu_vg_h2(h2_from_f32(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+            pw[i] = h2_bits(__hmul2(vg.grad, w4h[h2 * 8 + i]));
+            aw[i] = h2_bits(vg.value);
+          }
+          const uint32_t chunk = (((32 * e) & 63) >> 3) + 2 * h2;
+          const uint32_t o0 = ((chunk ^ (m & 7)) << 4), o1 = (((chunk + 1) ^ (m & 7)) << 4);
+          *reinterpret_cast<uint4*>(prow + o0) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(prow + o1) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+          *reinterpret_cast<uint4*>(arow + o0) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
+          *reinterpret_cast<uint4*>(arow + o1) = make_uint4(aw[4], aw[5], aw[6], aw[7]);
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&d1_empty[buf]); mbar_arrive(&p_full[pb]); }
+      // ---- dh tile: only the e == 0 warps read it back
+      if (e == 0) {
+        mbar_wait(&d2_full[pb], (n >> 1) & 1);
+        tcgen05_fence_after();
+        uint32_t v[16], w[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + pb * 48, v);
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + pb * 48 + 16, w);
+        tmem_ld_wait();
+        if (row_ok) {
+          __nv_bfloat16* gp = p.g + static_cast<long long>(b) * p.C * p.S + pos;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < p.C) gp[static_cast<long long>(i) * p.S] = __float2bfloat16(dout * __uint_as_float(i < 16 ? v[i & 15] : w[i & 15]));
+        }
+        if (p.C > 32) {                       // (not reachable with the supported widths; kept for KR = 48 layouts)
+          uint32_t x[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + pb * 48 + 32, x);
+          tmem_ld_wait();
+          if (row_ok) {
+            __nv_bfloat16* gp = p.g + static_cast<long long>(b) * p.C * p.S + pos;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (32 + i < p.C) gp[static_cast<long long>(32 + i) * p.S] = __float2bfloat16(dout * __uint_as_float(x[i]));
+          }
+        }
+        tcgen05_fence_before();
+      }
+      if (++s == kStagesHB) s = 0;
+    }
+    // ---- per-CTA flush of the weight gradients
+    acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 16);
+    acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 8);
+    acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 4);
+    acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 2);
+    acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 1);
+    if (lane == 0 && e == 0) atomicAdd(s_gb4, acc_gb4);
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiHB) : "memory");
+    if (n > 0 && e == 0) {
+      mbar_wait(all_done, 0);
+      tcgen05_fence_after();
+      const float inv = 1.0f / scale;
+      const int j = m;                                   // TMEM lane = hidden unit
+#pragma unroll
+      for (int cb = 0; cb < 3; ++cb) {
+        if (cb * 16 < p.KR) {
+          uint32_t v3[16], v4[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD3 + cb * 16, v3);
+          tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD4 + cb * 16, v4);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = cb * 16 + i;
+            if (c < p.C) atomicAdd(p.gW3 + j * p.C + c, __uint_as_float(v3[i]) * inv);
+            if (c == p.C) {
+              atomicAdd(p.gb3 + j, __uint_as_float(v3[i]) * inv);
+              atomicAdd(p.gW4 + j, __uint_as_float(v4[i]) * inv);
+            }
+          }
+        }
+      }
+      if (j == 0) atomicAdd(p.gb4, s_gb4[0]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kColsHd>(tmem_base);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ out) {
+  float mx = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i * 4 < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i * 4 + 3 < n) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    } else {
+      for (long long k = i * 4; k < n; ++k) mx = fmaxf(mx, fabsf(x[k]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out, __float_as_uint(mx));   // non-negative floats order like uints
+}
+
+int set_rowmap(RowMap* mp, int nrl, const int* R, const long long* SR) {
+  if (nrl < 1 || nrl > 4) return -1;
+  mp->nrl = nrl;
+  for (int i = 0; i < 4; ++i) { mp->R[i] = i < nrl ? R[i] : 1; mp->SR[i] = i < nrl ? SR[i] : 0; }
+  fill_magic(mp);
+  return 0;
+}
+
+}  // namespace
+
+// h: bf16 [B*C, S] channel-major; W3aug: bf16 [128, 64] with column C = b3; w4b4: fp32 [129]; out: fp32, addressed
+// through the row digits (row = b*S + position).
+const char* head_fwd(const void* h, const void* W3aug, const float* w4b4, float* out, int B, int C, long long S,
+                     int nrl, const int* R, const long long* SR, int num_sms, cudaStream_t stream) {
+  if (C < 1 || C > 47) return "head_fwd: 1 <= C <= 47";
+  if (S % 8 || S > (1ll << 31) - 256 || static_cast<long long>(B) * S > (1ll << 31) - 256) return "head_fwd: bad slab size";
+  HeadFwdParams p{};
+  p.B = B; p.C = C; p.KR = (C + 1 + 15) / 16 * 16; p.S = S; p.tiles_per_b = (S + 127) / 128;
+  p.w4b4 = w4b4; p.out = out;
+  if (set_rowmap(&p.map, nrl, R, SR)) return "head_fwd: 1..4 row digits";
+  CUtensorMap tmH, tmW3;
+  if (make_map_2d(&tmH, h, S, static_cast<uint64_t>(B) * C, S, 64, C)) return "tensor map (h) failed";
+  if (make_map_2d(&tmW3, W3aug, 64, 128, 64, 64, 128)) return "tensor map (W3) failed";
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return "cudaFuncSetAttribute failed";
+    attr = true;
+  }
+  const uint32_t smem_bytes = 16384 + kStagesHF * 2 * p.KR * 128 + 2048 + 1024;
+  const long long tiles = p.tiles_per_b * B;
+  const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  head_fwd_kernel<<<grid, kThreadsHF, smem_bytes > 120 * 1024 ? smem_bytes : 120 * 1024, stream>>>(tmH, tmW3, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// W3T16: fp16 [KR, 128] (rows = input channel, zero padded); dout: fp32 public layout; amax_ws: one uint of scratch
+// (receives max |dout|); g: bf16 [B*C, S]; gradients are accumulated with atomics.
+const char* head_bwd2(const void* h, const void* W3aug, const void* W3T16, const float* W4, const float* dout,
+                      long long n_dout, unsigned* amax_ws, void* g, float* gW3, float* gb3, float* gW4, float* gb4,
+                      int B, int C, long long S, int nrl, const int* R, const long long* SR, int num_sms,
+                      cudaStream_t stream) {
+  if (C < 1 || C > 47) return "head_bwd: 1 <= C <= 47";
+  if (S % 8 || S > (1ll << 31) - 256 || static_cast<long long>(B) * S > (1ll << 31) - 256) return "head_bwd: bad slab size";
+  HeadBwdParams p{};
+  p.B = B; p.C = C; p.KR = (C + 1 + 15) / 16 * 16; p.S = S; p.tiles_per_b = (S + 127) / 128;
+  p.dout = dout; p.amax = reinterpret_cast<const float*>(amax_ws); p.W4 = W4;
+  p.g = static_cast<__nv_bfloat16*>(g); p.gW3 = gW3; p.gb3 = gb3; p.gW4 = gW4; p.gb4 = gb4;
+  if (set_rowmap(&p.map, nrl, R, SR)) return "head_bwd: 1..4 row digits";
+  CUtensorMap tmH, tmW3, tmW3T;
+  if (make_map_2d(&tmH, h, S, static_cast<uint64_t>(B) * C, S, 64, C)) return "tensor map (h) failed";
+  if (make_map_2d(&tmW3, W3aug, 64, 128, 64, 64, 128)) return "tensor map (W3) failed";
+  if (make_map_2d(&tmW3T, W3T16, 128, p.KR, 128, 64, p.KR)) return "tensor map (W3T) failed";
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(head_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return "cudaFuncSetAttribute failed";
+    attr = true;
+  }
+  if (cudaMemsetAsync(amax_ws, 0, 4, stream) != cudaSuccess) return "head_bwd: memset failed";
+  absmax_kernel<<<num_sms * 4, 256, 0, stream>>>(dout, n_dout, amax_ws);
+  const uint32_t tile_bytes = 2u * p.KR * 128;
+  const uint32_t smem_bytes = 16384 + tile_bytes + 131072 + (kStagesHB + 2) * tile_bytes + 2048 + 1024;
+  const long long tiles = p.tiles_per_b * B;
+  const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  head_bwd2_kernel<<<grid, kThreadsHB, smem_bytes, stream>>>(tmH, tmW3, tmW3T, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace dfno

@@ -22,6 +22,7 @@ const char* permute_u32(const void* src, void* dst, int nd, const int* size, con
                         const long long* dstr, int num_sms, cudaStream_t s);
 // device GELU / GELU' evaluated on a vector (accuracy probe for the tests)
 const char* gelu_probe(const float* x, float* y, float* dy, long long n, cudaStream_t s);
+const char* gelu_probe_h2(const float* x, float* y, float* dy, long long n, cudaStream_t s);   // packed fp16 variant (n even)
 // S = X*Y*T*Z elements per (b, c) slab.  out / out_cl may be null.
 const char* bypass_gelu_fwd(const void* h, void* spec_pre, const float* W, void* out, void* out_cl, int cl_pitch,
                             int B, int C, long long S, int save_pre, int num_sms, cudaStream_t s);
@@ -70,5 +71,22 @@ const char* kreduce_gemm(const void* A, long long lda, int Ma, const void* Bm, l
 const char* head_bwd(const void* hcl, long long npos, int C, int CP, const void* W3pad, const void* W3Tpad,
                      const float* b3, const float* W4, const float* dout, int nrl, const int* R, const long long* SR,
                      void* gcl, float* gW3, float* gb3, float* gW4, float* gb4, int num_sms, cudaStream_t stream);
+
+// ---- round-2 fused pointwise path (spectral_out_sm100.cu, dpre_dw_sm100.cu, head_sm100.cu) ----
+// Last stage of a Fourier layer + bypass conv (+ GELU): see spectral_out_sm100.cu.  U: bf16 [B*C, L, K1];
+// h / pre / out: bf16 [B*C, L, Z]; Bop: padded operator bf16 [n_pad, k_pad]; W: fp32 [C, C].
+const char* spectral_out(const void* U, const void* h, const void* Bop, int n_pad, int k_pad, const float* W,
+                         int transpose_w, void* pre, void* out, int B, int C, long long L, int Z, int K1, int gelu,
+                         int save_pre, int num_sms, cudaStream_t stream);
+// dpre = g * gelu'(pre) (in place over pre); dW += dpre . h^T
+const char* dpre_dw(const void* g, void* pre_dpre, const void* h, float* dW, int B, int C, long long L, int Z,
+                    int num_sms, cudaStream_t stream);
+// projection head on the channel-major activation (head_sm100.cu)
+const char* head_fwd(const void* h, const void* W3aug, const float* w4b4, float* out, int B, int C, long long S,
+                     int nrl, const int* R, const long long* SR, int num_sms, cudaStream_t stream);
+const char* head_bwd2(const void* h, const void* W3aug, const void* W3T16, const float* W4, const float* dout,
+                      long long n_dout, unsigned* amax_ws, void* g, float* gW3, float* gb3, float* gW4, float* gb4,
+                      int B, int C, long long S, int nrl, const int* R, const long long* SR, int num_sms,
+                      cudaStream_t stream);
 
 }  // namespace dfno

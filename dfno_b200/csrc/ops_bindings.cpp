@@ -196,6 +196,14 @@ std::vector<at::Tensor> gelu_probe(const at::Tensor& x) {
   return {y, dy};
 }
 
+std::vector<at::Tensor> gelu_probe_h2(const at::Tensor& x) {
+  TORCH_CHECK(x.numel() % 2 == 0, "even length");
+  c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor y = at::empty_like(x), dy = at::empty_like(x);
+  check(dfno::gelu_probe_h2(fptr(x), y.data_ptr<float>(), dy.data_ptr<float>(), x.numel(), cur_stream()), "gelu_probe_h2");
+  return {y, dy};
+}
+
 void head_bwd(const at::Tensor& hcl, int64_t npos, int64_t C, int64_t CP, const at::Tensor& W3pad,
               const at::Tensor& W3Tpad, const at::Tensor& b3, const at::Tensor& W4, const at::Tensor& dout,
               const std::vector<int64_t>& radices, const std::vector<int64_t>& strides, at::Tensor& gcl,
@@ -211,9 +219,61 @@ void head_bwd(const at::Tensor& hcl, int64_t npos, int64_t C, int64_t CP, const 
                        fptr_mut(gb3), fptr_mut(gW4), fptr_mut(gb4), sm_count(), cur_stream()), "head_bwd");
 }
 
+void spectral_out(const at::Tensor& U, const at::Tensor& h, const at::Tensor& Bop, const at::Tensor& W, bool transpose_w,
+                  const c10::optional<at::Tensor>& pre, at::Tensor& out, int64_t B, int64_t C, int64_t L, int64_t Z,
+                  int64_t K1, bool gelu, bool save_pre) {
+  TORCH_CHECK(Bop.dim() == 2 && Bop.is_contiguous(), "operator must be a contiguous [n_pad, k_pad] tensor");
+  c10::cuda::CUDAGuard guard(U.device());
+  check(dfno::spectral_out(bptr(U), bptr(h), bptr(Bop), static_cast<int>(Bop.size(0)), static_cast<int>(Bop.size(1)),
+                           fptr(W), transpose_w ? 1 : 0, pre ? bptr(*pre) : nullptr, bptr(out), static_cast<int>(B),
+                           static_cast<int>(C), L, static_cast<int>(Z), static_cast<int>(K1), gelu ? 1 : 0,
+                           save_pre ? 1 : 0, sm_count(), cur_stream()), "spectral_out");
+}
+
+void dpre_dw(const at::Tensor& g, at::Tensor& pre_dpre, const at::Tensor& h, at::Tensor& dW, int64_t B, int64_t C,
+             int64_t L, int64_t Z) {
+  c10::cuda::CUDAGuard guard(g.device());
+  check(dfno::dpre_dw(bptr(g), bptr(pre_dpre), bptr(h), fptr_mut(dW), static_cast<int>(B), static_cast<int>(C), L,
+                      static_cast<int>(Z), sm_count(), cur_stream()), "dpre_dw");
+}
+
+void head_fwd(const at::Tensor& h, const at::Tensor& W3aug, const at::Tensor& w4b4, at::Tensor& out, int64_t B,
+              int64_t C, int64_t S, const std::vector<int64_t>& radices, const std::vector<int64_t>& strides) {
+  TORCH_CHECK(radices.size() == strides.size() && !radices.empty() && radices.size() <= 4, "1..4 row digits");
+  TORCH_CHECK(W3aug.dim() == 2 && W3aug.size(0) == 128 && W3aug.size(1) == 64 && W3aug.is_contiguous(), "W3aug [128,64]");
+  TORCH_CHECK(w4b4.numel() >= 129, "w4b4 = [W4 (128), b4]");
+  c10::cuda::CUDAGuard guard(h.device());
+  int R[4]; long long SR[4];
+  for (size_t i = 0; i < 4; ++i) { R[i] = i < radices.size() ? static_cast<int>(radices[i]) : 1; SR[i] = i < strides.size() ? strides[i] : 0; }
+  check(dfno::head_fwd(bptr(h), bptr(W3aug), fptr(w4b4), fptr_mut(out), static_cast<int>(B), static_cast<int>(C), S,
+                       static_cast<int>(radices.size()), R, SR, sm_count(), cur_stream()), "head_fwd");
+}
+
+void head_bwd2(const at::Tensor& h, const at::Tensor& W3aug, const at::Tensor& W3T16, const at::Tensor& W4,
+               const at::Tensor& dout, at::Tensor& amax_ws, at::Tensor& g, at::Tensor& gW3, at::Tensor& gb3,
+               at::Tensor& gW4, at::Tensor& gb4, int64_t B, int64_t C, int64_t S, const std::vector<int64_t>& radices,
+               const std::vector<int64_t>& strides) {
+  TORCH_CHECK(radices.size() == strides.size() && !radices.empty() && radices.size() <= 4, "1..4 row digits");
+  TORCH_CHECK(W3aug.dim() == 2 && W3aug.size(0) == 128 && W3aug.size(1) == 64 && W3aug.is_contiguous(), "W3aug [128,64]");
+  TORCH_CHECK(W3T16.is_cuda() && W3T16.scalar_type() == at::kHalf && W3T16.dim() == 2 && W3T16.size(1) == 128 &&
+              W3T16.size(0) == (C + 1 + 15) / 16 * 16 && W3T16.is_contiguous(), "W3T16: fp16 [ceil16(C+1), 128]");
+  TORCH_CHECK(amax_ws.is_cuda() && amax_ws.numel() >= 1 && amax_ws.element_size() == 4, "amax_ws: one 32-bit word");
+  c10::cuda::CUDAGuard guard(h.device());
+  int R[4]; long long SR[4];
+  for (size_t i = 0; i < 4; ++i) { R[i] = i < radices.size() ? static_cast<int>(radices[i]) : 1; SR[i] = i < strides.size() ? strides[i] : 0; }
+  check(dfno::head_bwd2(bptr(h), bptr(W3aug), W3T16.data_ptr(), fptr(W4), fptr(dout), dout.numel(),
+                        reinterpret_cast<unsigned*>(amax_ws.data_ptr()), bptr(g), fptr_mut(gW3), fptr_mut(gb3),
+                        fptr_mut(gW4), fptr_mut(gb4), static_cast<int>(B), static_cast<int>(C), S,
+                        static_cast<int>(radices.size()), R, SR, sm_count(), cur_stream()), "head_bwd2");
+}
+
 }  // namespace
 
 void register_ops(pybind11::module& m) {
+  m.def("spectral_out", &spectral_out);
+  m.def("dpre_dw", &dpre_dw);
+  m.def("head_fwd", &head_fwd);
+  m.def("head_bwd2", &head_bwd2);
   m.def("lift_fwd", &lift_fwd);
   m.def("lift_bwd", &lift_bwd);
   m.def("bypass_gelu_fwd", &bypass_gelu_fwd);
@@ -231,6 +291,7 @@ void register_ops(pybind11::module& m) {
   m.def("kreduce_gemm", &kreduce_gemm);
   m.def("head_bwd", &head_bwd);
   m.def("gelu_probe", &gelu_probe);
+  m.def("gelu_probe_h2", &gelu_probe_h2);
   m.def("permute_u32", &permute_u32);
   m.def("tma_probe_4d", &tma_probe_4d);
 }

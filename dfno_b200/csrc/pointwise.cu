@@ -34,89 +34,129 @@ __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { re
 // ------------------------------------------------------------------------------------------
 // lift
 // ------------------------------------------------------------------------------------------
-constexpr int kLiftMaxIn = 32;     // Cin * Tin values per position kept in registers
-constexpr int kLiftMaxW = 4096;    // floats of shared memory for W1,b1,W2,b2
+// One thread owns 8 consecutive z of one (b, x, y) -- a 16-byte bf16 vector of every output row it produces,
+// so a warp writes whole 256-byte z-lines -- and walks t and c.  Both GELUs run in packed fp16 (sm100_ptx.cuh):
+// the outer one is evaluated B*C*X*Y*Z*T times per step.  The few input values a thread needs stay in
+// registers when Tin == 1 (the benchmark / two-phase case) and are re-read through L1 otherwise (Cin <= 4, Tin <= 64).
+constexpr int kLiftMaxTin = 64;
+constexpr int kLiftMaxW = 4096;    // floats of shared memory for W1, b1 (+ packed W2, b2)
 
 template <typename TIn>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void lift_load8(const TIn* __restrict__ src, int Tin, int ti, float (&v)[8]) {
+#pragma unroll
+  for (int z = 0; z < 8; ++z) v[z] = ldf(src + z * Tin + ti);
+}
+template <>
+__device__ __forceinline__ void lift_load8<float>(const float* __restrict__ src, int Tin, int ti, float (&v)[8]) {
+  if (Tin == 1) {
+    const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int z = 0; z < 8; ++z) v[z] = src[z * Tin + ti];
+  }
+}
+
+// v1[z] = b1[t] + sum_ti W1[t, ti] x[ci, z, ti]
+template <typename TIn, bool kRegs>
+__device__ __forceinline__ void lift_inner(const TIn* __restrict__ xci, const float (*xr)[8], int ci, int Tin,
+                                           const float* sW1t, float b1t, float (&v)[8]) {
+#pragma unroll
+  for (int z = 0; z < 8; ++z) v[z] = b1t;
+  for (int ti = 0; ti < Tin; ++ti) {
+    float xv[8];
+    if (kRegs) {                        // Tin == 1
+#pragma unroll
+      for (int z = 0; z < 8; ++z) xv[z] = xr[ci][z];
+    } else {
+      lift_load8<TIn>(xci, Tin, ti, xv);
+    }
+    const float w = sW1t[ti];
+#pragma unroll
+    for (int z = 0; z < 8; ++z) v[z] = fmaf(w, xv[z], v[z]);
+  }
+}
+
+template <typename TIn, int CIN, bool kRegs>
+__global__ void __launch_bounds__(256)
 lift_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1,
                 const float* __restrict__ W2, const float* __restrict__ b2, __nv_bfloat16* __restrict__ h,
                 LiftDims d) {
   __shared__ float sw[kLiftMaxW];
-  float* sW1 = sw;                         // [T][Tin]
-  float* sb1 = sW1 + d.T * d.Tin;          // [T]
-  float* sW2 = sb1 + d.T;                  // [C][Cin]
-  float* sb2 = sW2 + d.C * d.Cin;          // [C]
+  float* sW1 = sw;                                          // [T][Tin]
+  float* sb1 = sW1 + d.T * d.Tin;                           // [T]
+  __half2* sW2 = reinterpret_cast<__half2*>(sb1 + d.T);     // [C][CIN] (value duplicated in both halves)
+  __half2* sb2 = sW2 + d.C * CIN;                           // [C]
   for (int i = threadIdx.x; i < d.T * d.Tin; i += blockDim.x) sW1[i] = W1[i];
   for (int i = threadIdx.x; i < d.T; i += blockDim.x) sb1[i] = b1[i];
-  for (int i = threadIdx.x; i < d.C * d.Cin; i += blockDim.x) sW2[i] = W2[i];
-  for (int i = threadIdx.x; i < d.C; i += blockDim.x) sb2[i] = b2[i];
+  for (int i = threadIdx.x; i < d.C * CIN; i += blockDim.x) sW2[i] = __float2half2_rn(W2[i]);
+  for (int i = threadIdx.x; i < d.C; i += blockDim.x) sb2[i] = __float2half2_rn(b2[i]);
   __syncthreads();
 
-  const int zp = d.Z >> 1;                              // z pairs
-  const long long npos = static_cast<long long>(d.B) * d.X * d.Y * zp;
-  const long long plane = static_cast<long long>(d.X) * d.Y;   // (x,y) positions
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < npos;
+  const int zv = d.Z >> 3;
+  const long long plane = static_cast<long long>(d.X) * d.Y;
+  const long long nitems = static_cast<long long>(d.B) * plane * zv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < nitems;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int z2 = static_cast<int>(idx % zp);
-    const long long xy = (idx / zp) % plane;
-    const int b = static_cast<int>(idx / (zp * plane));
-    float xin[2][kLiftMaxIn];
+    const int z0 = static_cast<int>(idx % zv) * 8;
+    const long long xy = (idx / zv) % plane;
+    const int b = static_cast<int>(idx / (zv * plane));
+    const TIn* xb = x + (((static_cast<long long>(b) * CIN) * plane + xy) * d.Z + z0) * d.Tin;
+    const long long xci_stride = plane * d.Z * d.Tin;
+    float xr[kRegs ? CIN : 1][8];
+    if (kRegs) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      for (int ci = 0; ci < d.Cin; ++ci) {
-        const TIn* src = x + ((((static_cast<long long>(b) * d.Cin + ci) * plane + xy) * d.Z) + (2 * z2 + q)) * d.Tin;
-        for (int ti = 0; ti < d.Tin; ++ti) xin[q][ci * d.Tin + ti] = ldf(src + ti);
-      }
+      for (int ci = 0; ci < CIN; ++ci) lift_load8<TIn>(xb + ci * xci_stride, 1, 0, xr[ci]);
     }
+    __nv_bfloat16* hb = h + ((static_cast<long long>(b) * d.C * plane + xy) * d.T) * d.Z + z0;
+    const long long hc_stride = plane * d.T * d.Z;
     for (int t = 0; t < d.T; ++t) {
-      float a1[2][8];
-      for (int ci = 0; ci < d.Cin; ++ci) {
+      __half2 a1[CIN][4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float v = sb1[t];
-          for (int ti = 0; ti < d.Tin; ++ti) v = fmaf(sW1[t * d.Tin + ti], xin[q][ci * d.Tin + ti], v);
-          a1[q][ci] = gelu_erf(v);
-        }
+      for (int ci = 0; ci < CIN; ++ci) {
+        float v[8];
+        lift_inner<TIn, kRegs>(xb + ci * xci_stride, xr, ci, d.Tin, sW1 + t * d.Tin, sb1[t], v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a1[ci][k] = gelu_h2(h2_from_f32(v[2 * k], v[2 * k + 1]));
       }
       for (int c = 0; c < d.C; ++c) {
-        float v0 = sb2[c], v1 = sb2[c];
-        for (int ci = 0; ci < d.Cin; ++ci) {
-          v0 = fmaf(sW2[c * d.Cin + ci], a1[0][ci], v0);
-          v1 = fmaf(sW2[c * d.Cin + ci], a1[1][ci], v1);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __half2 acc = sb2[c];
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) acc = __hfma2(sW2[c * CIN + ci], a1[ci][k], acc);
+          o[k] = h2_to_bf16x2(gelu_h2(acc));
         }
-        __nv_bfloat16* dst = h + ((((static_cast<long long>(b) * d.C + c) * plane + xy) * d.T + t) * d.Z) + 2 * z2;
-        *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(gelu_erf(v0), gelu_erf(v1));
+        *reinterpret_cast<uint4*>(hb + c * hc_stride + static_cast<long long>(t) * d.Z) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
 }
 
-// dW1[T][Tin], db1[T], dW2[C][Cin], db2[C] accumulated with atomics into fp32 buffers.
-// Channel-indexed sums (db2, dW2) stay in registers over the whole grid-stride loop and are
-// reduced once per thread; time-indexed sums (db1, dW1) are warp-reduced once per t.
-template <typename TIn, int C, int CIN>
+// dW1[T][Tin], db1[T], dW2[C][Cin], db2[C] accumulated with atomics into fp32 buffers.  Channel-indexed sums
+// stay in registers over the whole grid-stride loop; time-indexed sums are warp-reduced once per t.  The loss
+// gradient can be far below the fp16 range, so everything it multiplies is fp32; only the GELU' evaluations
+// are packed fp16.
+template <typename TIn, int C, int CIN, bool kRegs>
 __global__ void __launch_bounds__(128)
 lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1,
                 const float* __restrict__ W2, const float* __restrict__ b2,
                 const __nv_bfloat16* __restrict__ dh, float* __restrict__ gW1, float* __restrict__ gb1,
                 float* __restrict__ gW2, float* __restrict__ gb2, LiftDims d) {
   __shared__ float sw[kLiftMaxW];
-  __shared__ float sg[kLiftMaxW];          // block-local gradient accumulators, same layout
+  __shared__ float sg[kLiftMaxW];
   float* sW1 = sw;
   float* sb1 = sW1 + d.T * d.Tin;
-  float* sW2 = sb1 + d.T;
-  float* sb2 = sW2 + C * CIN;
-  const int nW = d.T * d.Tin + d.T + C * CIN + C;
+  float* sW2f = sb1 + d.T;                                   // [C][CIN] fp32 (input-gradient path)
+  __half2* sW2 = reinterpret_cast<__half2*>(sW2f + C * CIN); // [C][CIN] packed fp16 (recomputation)
+  __half2* sb2 = sW2 + C * CIN;
   float* gsW1 = sg;
   float* gsb1 = gsW1 + d.T * d.Tin;
-  float* gsW2 = gsb1 + d.T;
-  float* gsb2 = gsW2 + C * CIN;
-  for (int i = threadIdx.x; i < d.T * d.Tin; i += blockDim.x) sW1[i] = W1[i];
-  for (int i = threadIdx.x; i < d.T; i += blockDim.x) sb1[i] = b1[i];
-  for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) sW2[i] = W2[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sb2[i] = b2[i];
-  for (int i = threadIdx.x; i < nW; i += blockDim.x) sg[i] = 0.f;
+  for (int i = threadIdx.x; i < d.T * d.Tin; i += blockDim.x) { sW1[i] = W1[i]; gsW1[i] = 0.f; }
+  for (int i = threadIdx.x; i < d.T; i += blockDim.x) { sb1[i] = b1[i]; gsb1[i] = 0.f; }
+  for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) { sW2f[i] = W2[i]; sW2[i] = __float2half2_rn(W2[i]); }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sb2[i] = __float2half2_rn(b2[i]);
   __syncthreads();
 
   float accb2[C], accW2[C][CIN];
@@ -126,83 +166,116 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) accW2[c][ci] = 0.f;
   }
-
   const int lane = threadIdx.x & 31;
-  const int zp = d.Z >> 1;
-  const long long npos = static_cast<long long>(d.B) * d.X * d.Y * zp;
+  const int zv = d.Z >> 3;
   const long long plane = static_cast<long long>(d.X) * d.Y;
-  const long long nloop = (npos + static_cast<long long>(gridDim.x) * blockDim.x - 1) /
-                          (static_cast<long long>(gridDim.x) * blockDim.x);
+  const long long nitems = static_cast<long long>(d.B) * plane * zv;
+  const long long per_it = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nloop = (nitems + per_it - 1) / per_it;
   for (long long it = 0; it < nloop; ++it) {
-    const long long idx = (it * gridDim.x + blockIdx.x) * static_cast<long long>(blockDim.x) + threadIdx.x;
-    const bool ok = idx < npos;                          // whole warps stay in the loop (shuffles)
+    const long long idx = it * per_it + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const bool ok = idx < nitems;                           // whole warps stay in the loop (shuffles)
     const long long id = ok ? idx : 0;
-    const int z2 = static_cast<int>(id % zp);
-    const long long xy = (id / zp) % plane;
-    const int b = static_cast<int>(id / (zp * plane));
-    float xin[2][kLiftMaxIn];
+    const int z0 = static_cast<int>(id % zv) * 8;
+    const long long xy = (id / zv) % plane;
+    const int b = static_cast<int>(id / (zv * plane));
+    const TIn* xb = x + (((static_cast<long long>(b) * CIN) * plane + xy) * d.Z + z0) * d.Tin;
+    const long long xci_stride = plane * d.Z * d.Tin;
+    float xr[kRegs ? CIN : 1][8];
+    if (kRegs) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) {
-        const TIn* src = x + ((((static_cast<long long>(b) * CIN + ci) * plane + xy) * d.Z) + (2 * z2 + q)) * d.Tin;
-        for (int ti = 0; ti < d.Tin; ++ti) xin[q][ci * d.Tin + ti] = ok ? ldf(src + ti) : 0.f;
-      }
+      for (int ci = 0; ci < CIN; ++ci) lift_load8<TIn>(xb + ci * xci_stride, 1, 0, xr[ci]);
+    }
+    const __nv_bfloat16* gb = dh + ((static_cast<long long>(b) * C * plane + xy) * d.T) * d.Z + z0;
+    const long long hc_stride = plane * d.T * d.Z;
     for (int t = 0; t < d.T; ++t) {
-      float a1[2][CIN], g1p[2][CIN], da1[2][CIN];
+      __half2 a1[CIN][4];
+      float a1f[CIN][8], g1f[CIN][8], da1[CIN][8];
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
+        float v[8];
+        lift_inner<TIn, kRegs>(xb + ci * xci_stride, xr, ci, d.Tin, sW1 + t * d.Tin, sb1[t], v);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float v = sb1[t];
-          for (int ti = 0; ti < d.Tin; ++ti) v = fmaf(sW1[t * d.Tin + ti], xin[q][ci * d.Tin + ti], v);
-          a1[q][ci] = gelu_erf(v);
-          g1p[q][ci] = gelu_erf_grad(v);
-          da1[q][ci] = 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const GeluH2 vg = gelu_vg_h2(h2_from_f32(v[2 * k], v[2 * k + 1]));
+          a1[ci][k] = vg.value;
+          const float2 av = __half22float2(vg.value), gv = __half22float2(vg.grad);
+          a1f[ci][2 * k] = av.x; a1f[ci][2 * k + 1] = av.y;
+          g1f[ci][2 * k] = gv.x; g1f[ci][2 * k + 1] = gv.y;
+          da1[ci][2 * k] = 0.f; da1[ci][2 * k + 1] = 0.f;
         }
       }
-      const __nv_bfloat16* src = dh + (((static_cast<long long>(b) * C * plane + xy) * d.T + t) * d.Z) + 2 * z2;
-      const long long cstride = plane * d.T * d.Z;
-      uint32_t gv[C];                                     // all channel loads of this t in flight together
+      static_assert(C % 4 == 0, "channels are processed four at a time");
 #pragma unroll
-      for (int c = 0; c < C; ++c) gv[c] = ok ? *reinterpret_cast<const uint32_t*>(src + c * cstride) : 0u;
+      for (int c4 = 0; c4 < C; c4 += 4) {
+        uint4 gv[4];                                        // four channel loads in flight together
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float v0 = sb2[c], v1 = sb2[c];
+        for (int u = 0; u < 4; ++u)
+          gv[u] = ok ? *reinterpret_cast<const uint4*>(gb + (c4 + u) * hc_stride + static_cast<long long>(t) * d.Z)
+                     : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-          v0 = fmaf(sW2[c * CIN + ci], a1[0][ci], v0);
-          v1 = fmaf(sW2[c * CIN + ci], a1[1][ci], v1);
-        }
-        const float2 g = unpack_bf16x2(gv[c]);
-        const float g0 = g.x * gelu_erf_grad(v0);
-        const float g1 = g.y * gelu_erf_grad(v1);
-        accb2[c] += g0 + g1;
+        for (int u = 0; u < 4; ++u) {
+          const int c = c4 + u;
+          const uint32_t gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+          float dv[8];
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-          accW2[c][ci] += g0 * a1[0][ci] + g1 * a1[1][ci];
-          da1[0][ci] = fmaf(sW2[c * CIN + ci], g0, da1[0][ci]);
-          da1[1][ci] = fmaf(sW2[c * CIN + ci], g1, da1[1][ci]);
+          for (int k = 0; k < 4; ++k) {
+            __half2 acc = sb2[c];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) acc = __hfma2(sW2[c * CIN + ci], a1[ci][k], acc);
+            const float2 gr = __half22float2(gelu_vg_h2(acc).grad);
+            const float2 g = unpack_bf16x2(gw[k]);
+            dv[2 * k] = g.x * gr.x; dv[2 * k + 1] = g.y * gr.y;
+          }
+          float sb = 0.f;
+#pragma unroll
+          for (int z = 0; z < 8; ++z) sb += dv[z];
+          accb2[c] += sb;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float w = sW2f[c * CIN + ci];
+            float sacc = 0.f;
+#pragma unroll
+            for (int z = 0; z < 8; ++z) {
+              sacc = fmaf(dv[z], a1f[ci][z], sacc);
+              da1[ci][z] = fmaf(w, dv[z], da1[ci][z]);
+            }
+            accW2[c][ci] += sacc;
+          }
         }
       }
       float sb1v = 0.f;
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        const float e0 = da1[0][ci] * g1p[0][ci], e1 = da1[1][ci] * g1p[1][ci];
-        sb1v += e0 + e1;
+        float e[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) { e[z] = da1[ci][z] * g1f[ci][z]; sb1v += e[z]; }
         for (int ti = 0; ti < d.Tin; ++ti) {
-          float sres = warp_sum(e0 * xin[0][ci * d.Tin + ti] + e1 * xin[1][ci * d.Tin + ti]);
+          float xv[8];
+          if (kRegs) {
+#pragma unroll
+            for (int z = 0; z < 8; ++z) xv[z] = xr[ci][z];
+          } else {
+            lift_load8<TIn>(xb + ci * xci_stride, d.Tin, ti, xv);
+          }
+          float sres = 0.f;
+#pragma unroll
+          for (int z = 0; z < 8; ++z) sres = fmaf(e[z], xv[z], sres);
+          sres = warp_sum(ok ? sres : 0.f);
           if (lane == 0) atomicAdd(&gsW1[t * d.Tin + ti], sres);
         }
       }
-      sb1v = warp_sum(sb1v);
+      sb1v = warp_sum(ok ? sb1v : 0.f);
       if (lane == 0) atomicAdd(&gsb1[t], sb1v);
     }
   }
+  __shared__ float gsW2[64 * 4 + 64];
+  for (int i = threadIdx.x; i < C * CIN + C; i += blockDim.x) gsW2[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const float sres = warp_sum(accb2[c]);
-    if (lane == 0) atomicAdd(&gsb2[c], sres);
+    if (lane == 0) atomicAdd(&gsW2[C * CIN + c], sres);
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
       const float sw2 = warp_sum(accW2[c][ci]);
@@ -213,7 +286,7 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
   for (int i = threadIdx.x; i < d.T * d.Tin; i += blockDim.x) atomicAdd(&gW1[i], gsW1[i]);
   for (int i = threadIdx.x; i < d.T; i += blockDim.x) atomicAdd(&gb1[i], gsb1[i]);
   for (int i = threadIdx.x; i < C * CIN; i += blockDim.x) atomicAdd(&gW2[i], gsW2[i]);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&gb2[i], gsb2[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&gb2[i], gsW2[C * CIN + i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -337,6 +410,17 @@ __global__ void gelu_probe_kernel(const float* __restrict__ x, float* __restrict
   if (i < n) { y[i] = gelu_erf(x[i]); dy[i] = gelu_erf_grad(x[i]); }
 }
 
+// the packed fp16 GELU the fused kernels use (pairs of adjacent elements)
+__global__ void gelu_probe_h2_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ dy, long long n) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const GeluH2 r = gelu_vg_h2(h2_from_f32(x[i], x[i + 1]));
+    const float2 v = __half22float2(r.value), g = __half22float2(r.grad);
+    const float2 v2 = __half22float2(gelu_h2(h2_from_f32(x[i], x[i + 1])));
+    y[i] = v.x; y[i + 1] = v2.y; dy[i] = g.x; dy[i + 1] = g.y;
+  }
+}
+
 // Generic strided permutation of 32-bit words (one (re, im) bf16 pair each): dst is walked in its
 // own mixed-radix order (innermost digit first), the same digits address src through src_strides.
 // Used on the receiving side of the fused pencil transposes: peers deposit their contribution as
@@ -447,25 +531,45 @@ const char* permute_u32(const void* src, void* dst, int nd, const int* size, con
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+const char* gelu_probe_h2(const float* x, float* y, float* dy, long long n, cudaStream_t s) {
+  gelu_probe_h2_kernel<<<static_cast<int>((n / 2 + 255) / 256), 256, 0, s>>>(x, y, dy, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
 const char* gelu_probe(const float* x, float* y, float* dy, long long n, cudaStream_t s) {
   gelu_probe_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(x, y, dy, n);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+static const char* lift_check(const LiftDims& d) {
+  if (d.Z % 8) return "lift: Z must be a multiple of 8";
+  if (d.Cin < 1 || d.Cin > 4) return "lift: supported input channel counts are 1..4";
+  if (d.Tin < 1 || d.Tin > kLiftMaxTin) return "lift: 1 <= Tin <= 64";
+  if (d.C > 64) return "lift: C <= 64";
+  if (d.T * d.Tin + d.T + 2 * (d.C * d.Cin + d.C) > kLiftMaxW) return "lift: weights exceed shared memory budget";
+  return nullptr;
+}
+
 const char* lift_fwd(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
                      const float* b2, void* h, LiftDims d, int num_sms, cudaStream_t s) {
-  if (d.Z % 2) return "Z must be even";
-  if (d.Cin * d.Tin > kLiftMaxIn || d.Cin > 8) return "lift: Cin*Tin too large for the fused kernel";
-  if (d.T * d.Tin + d.T + d.C * d.Cin + d.C > kLiftMaxW) return "lift: weights exceed shared memory budget";
-  const long long npos = static_cast<long long>(d.B) * d.X * d.Y * (d.Z / 2);
-  const int grid = grid_for(npos, 128, num_sms, 8);
-  if (x_is_bf16)
-    lift_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), W1, b1, W2, b2,
-                                                        static_cast<__nv_bfloat16*>(h), d);
-  else
-    lift_fwd_kernel<float><<<grid, 128, 0, s>>>(static_cast<const float*>(x), W1, b1, W2, b2,
-                                                static_cast<__nv_bfloat16*>(h), d);
+  if (const char* e = lift_check(d)) return e;
+  const long long nitems = static_cast<long long>(d.B) * d.X * d.Y * (d.Z / 8);
+  const int grid = grid_for(nitems, 256, num_sms, 4);
+  const bool regs = d.Tin == 1;
+#define DFNO_LIFT_FWD(T_, CIN_, R_) \
+  lift_fwd_kernel<T_, CIN_, R_><<<grid, 256, 0, s>>>(static_cast<const T_*>(x), W1, b1, W2, b2, static_cast<__nv_bfloat16*>(h), d)
+#define DFNO_LIFT_FWD_T(T_)                                                                         \
+  switch (d.Cin) {                                                                                  \
+    case 1: if (regs) DFNO_LIFT_FWD(T_, 1, true); else DFNO_LIFT_FWD(T_, 1, false); break;          \
+    case 2: if (regs) DFNO_LIFT_FWD(T_, 2, true); else DFNO_LIFT_FWD(T_, 2, false); break;          \
+    case 3: if (regs) DFNO_LIFT_FWD(T_, 3, true); else DFNO_LIFT_FWD(T_, 3, false); break;          \
+    default: if (regs) DFNO_LIFT_FWD(T_, 4, true); else DFNO_LIFT_FWD(T_, 4, false); break;         \
+  }
+  if (x_is_bf16) { DFNO_LIFT_FWD_T(__nv_bfloat16) } else { DFNO_LIFT_FWD_T(float) }
+#undef DFNO_LIFT_FWD_T
+#undef DFNO_LIFT_FWD
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -485,15 +589,13 @@ const char* lift_fwd(const void* x, int x_is_bf16, const float* W1, const float*
 template <int C>
 static const char* lift_bwd_cin(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
                                 const float* b2, const void* dh, float* gW1, float* gb1, float* gW2, float* gb2,
-                                LiftDims d, int grid, cudaStream_t s) {
-#define DFNO_LIFT_BWD(CIN_)                                                                                       \
-  if (x_is_bf16)                                                                                                  \
-    lift_bwd_kernel<__nv_bfloat16, C, CIN_><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), W1, b1, W2, \
-                                                                 b2, static_cast<const __nv_bfloat16*>(dh), gW1,  \
-                                                                 gb1, gW2, gb2, d);                               \
-  else                                                                                                            \
-    lift_bwd_kernel<float, C, CIN_><<<grid, 128, 0, s>>>(static_cast<const float*>(x), W1, b1, W2, b2,            \
-                                                         static_cast<const __nv_bfloat16*>(dh), gW1, gb1, gW2, gb2, d);
+                                LiftDims d, int grid, bool regs, cudaStream_t s) {
+#define DFNO_LIFT_BWD2(T_, CIN_, R_)                                                                              \
+  lift_bwd_kernel<T_, C, CIN_, R_><<<grid, 128, 0, s>>>(static_cast<const T_*>(x), W1, b1, W2, b2,                \
+                                                        static_cast<const __nv_bfloat16*>(dh), gW1, gb1, gW2, gb2, d)
+#define DFNO_LIFT_BWD(CIN_)                                                                    \
+  if (x_is_bf16) { if (regs) DFNO_LIFT_BWD2(__nv_bfloat16, CIN_, true); else DFNO_LIFT_BWD2(__nv_bfloat16, CIN_, false); } \
+  else { if (regs) DFNO_LIFT_BWD2(float, CIN_, true); else DFNO_LIFT_BWD2(float, CIN_, false); }
   switch (d.Cin) {
     case 1: DFNO_LIFT_BWD(1); break;
     case 2: DFNO_LIFT_BWD(2); break;
@@ -502,19 +604,19 @@ static const char* lift_bwd_cin(const void* x, int x_is_bf16, const float* W1, c
     default: return "lift_bwd: supported input channel counts are 1..4";
   }
 #undef DFNO_LIFT_BWD
+#undef DFNO_LIFT_BWD2
   return nullptr;
 }
 
 const char* lift_bwd(const void* x, int x_is_bf16, const float* W1, const float* b1, const float* W2,
                      const float* b2, const void* dh, float* gW1, float* gb1, float* gW2, float* gb2,
                      LiftDims d, int num_sms, cudaStream_t s) {
-  if (d.Z % 2) return "Z must be even";
-  if (d.Cin * d.Tin > kLiftMaxIn || d.Cin > 4) return "lift: Cin*Tin too large for the fused kernel";
-  if (d.T * d.Tin + d.T + d.C * d.Cin + d.C > kLiftMaxW) return "lift: weights exceed shared memory budget";
-  const long long npos = static_cast<long long>(d.B) * d.X * d.Y * (d.Z / 2);
-  const int grid = grid_for(npos, 128, num_sms, 4);
+  if (const char* e = lift_check(d)) return e;
+  const long long nitems = static_cast<long long>(d.B) * d.X * d.Y * (d.Z / 8);
+  const int grid = grid_for(nitems, 128, num_sms, 4);
+  const bool regs = d.Tin == 1;
   const char* err = nullptr;
-  DFNO_DISPATCH_C(d.C, (err = lift_bwd_cin<kC>(x, x_is_bf16, W1, b1, W2, b2, dh, gW1, gb1, gW2, gb2, d, grid, s)));
+  DFNO_DISPATCH_C(d.C, (err = lift_bwd_cin<kC>(x, x_is_bf16, W1, b1, W2, b2, dh, gW1, gb1, gW2, gb2, d, grid, regs, s)));
   if (err) return err;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

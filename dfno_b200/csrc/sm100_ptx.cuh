@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace dfno {
@@ -83,6 +84,35 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// 3-D tiled load: coordinates innermost first
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// tiled stores (shared -> global, bulk async-group completion); out-of-range parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1,
+                                             int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// the issuing thread's committed stores have finished READING shared memory (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// ... and are complete (globally performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation
@@ -293,6 +323,65 @@ __device__ __forceinline__ GeluVG gelu_value_grad(float x) {
   return GeluVG{x * r.half1pt, fmaf(0.5f * (x * s), gp, r.half1pt)};
 }
 #endif
+// ------------------------------------------------------------------------------------------
+// packed fp16 GELU: two values per instruction (HFMA2 / one MUFU.TANH.F16x2 per PAIR)
+// ------------------------------------------------------------------------------------------
+// The pointwise epilogues evaluate 10^9..10^10 GELUs per step and were issue bound with the fp32
+// erf form (~17 instr + 2 MUFU per value).  This is the tanh form fitted to the *erf* GELU
+//     Phi(x) ~ 0.5 (1 + tanh(x (a + b x^2 + c x^4))),  x^2 clamped at 64   (|gelu err| <= 2.6e-5 in exact
+// arithmetic) evaluated in fp16x2: 7 instr + 1 MUFU per PAIR for the value, 14 + 1 for value and
+// derivative.  fp16 (11-bit significand) keeps the absolute error of gelu / gelu' near 1e-3 * max(1,|x|),
+// below the bf16 rounding (2^-9 relative) applied to every stored activation.
+// Inputs beyond the fp16 range are handled by the clamp (x^2 = inf -> 64; tanh saturates).
+#define DFNO_H2C(v) __float2half2_rn(v)
+// saturating: |x| beyond the fp16 range becomes +-65504 instead of inf, so x * cdf(x) stays finite (0 or x)
+__device__ __forceinline__ __half2 h2_from_f32(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ __half2 h2_tanh(__half2 x) {
+  uint32_t r, xi = *reinterpret_cast<uint32_t*>(&x);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(xi));
+  return *reinterpret_cast<__half2*>(&r);
+}
+struct GeluH2 { __half2 value; __half2 grad; };
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+  const __half2 x2 = __hmin2(__hmul2(x, x), DFNO_H2C(64.0f));
+  __half2 g = __hfma2(DFNO_H2C(-3.51519787e-4f), x2, DFNO_H2C(3.70056658e-2f));
+  g = __hfma2(g, x2, DFNO_H2C(7.97507861e-1f));
+  const __half2 t = h2_tanh(__hmul2(x, g));
+  return __hmul2(x, __hfma2(DFNO_H2C(0.5f), t, DFNO_H2C(0.5f)));
+}
+__device__ __forceinline__ GeluH2 gelu_vg_h2(__half2 x) {
+  const __half2 x2 = __hmin2(__hmul2(x, x), DFNO_H2C(64.0f));
+  __half2 g = __hfma2(DFNO_H2C(-3.51519787e-4f), x2, DFNO_H2C(3.70056658e-2f));
+  g = __hfma2(g, x2, DFNO_H2C(7.97507861e-1f));
+  const __half2 t = h2_tanh(__hmul2(x, g));
+  const __half2 cdf = __hfma2(DFNO_H2C(0.5f), t, DFNO_H2C(0.5f));
+  __half2 gp = __hfma2(DFNO_H2C(5.0f * -3.51519787e-4f), x2, DFNO_H2C(3.0f * 3.70056658e-2f));
+  gp = __hfma2(gp, x2, DFNO_H2C(7.97507861e-1f));                 // d/dx [x g(x^2)]
+  const __half2 s = __hfma2(__hneg2(t), t, DFNO_H2C(1.0f));       // sech^2
+  const __half2 xs = __hmul2(__hmul2(x, s), DFNO_H2C(0.5f));
+  GeluH2 r;
+  r.value = __hmul2(x, cdf);
+  r.grad = __hfma2(xs, gp, cdf);
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __half2 h2_of_bits(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+// fp16x2 <-> bf16x2 (through fp32; values outside the fp16 range saturate to inf and are clamped by the GELU)
+__device__ __forceinline__ uint32_t h2_to_bf16x2(__half2 v) {
+  const float2 f = __half22float2(v);
+  __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ __half2 bf16x2_to_h2(uint32_t u) {
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u);
+  const float2 f = __bfloat1622float2(b);
+  return h2_from_f32(f.x, f.y);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

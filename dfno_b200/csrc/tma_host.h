@@ -39,5 +39,20 @@ inline int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// 3-D bf16 tensor map (innermost first): dims (d0, d1, d2), element strides of d1 and d2, box (b0, b1, b2).
+// SWIZZLE_128B: b0 * 2 bytes must be <= 128.  Loads zero-fill outside the tensor, stores are clipped.
+inline int make_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                       uint64_t s2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_elems * 2, s2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
 
 }  // namespace dfno

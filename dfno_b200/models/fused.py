@@ -451,20 +451,34 @@ class _LaunchCounter:
 
 
 class _FusedFn(torch.autograd.Function):
+    """Autograd edge of the engine.  The saved activations live in ONE engine-owned buffer set, so a backward is
+    only valid for the most recent saving forward: every such forward gets a generation number and a stale
+    backward raises instead of silently using another forward's activations (micro-batch accumulation must run
+    forward -> backward per micro-batch, with ``accumulate_grads``)."""
+
     @staticmethod
-    def forward(ctx, x, theta, eng):
+    def forward(ctx, x, theta, eng, save):
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("the fused engine does not produce input gradients (dL/dx); use backend='torch' "
+                               "or detach the input")
         ctx.eng = eng
-        ctx.train = torch.is_grad_enabled() and theta.requires_grad
-        y = eng._forward(x, save=theta.requires_grad)
+        if save:
+            eng._generation += 1
+        ctx.generation = eng._generation if save else -1
+        y = eng._forward(x, save=save)
         ctx.save_for_backward(x)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
+        eng = ctx.eng
+        if ctx.generation != eng._generation:
+            raise RuntimeError("backward through a fused-engine forward whose saved activations were overwritten by a "
+                               "later forward (the engine keeps one set); run forward/backward pairs back to back")
         # the engine writes straight into theta.grad's storage (no 2 GB autograd copy)
-        ctx.eng._backward(x, dy)
-        return None, None, None
+        eng._backward(x, dy)
+        return None, None, None, None
 
 
 class FusedDistributedFNO(nn.Module):
@@ -540,6 +554,7 @@ class FusedDistributedFNO(nn.Module):
         }
         self._saved: Dict[str, torch.Tensor] = {}
         self._train_bufs_ready = False
+        self._generation = 0                     # number of saving forwards so far (see _FusedFn)
         # staged peer layout (long NVLink runs + local permutation): measured win at 8 GPUs (exposed
         # all-to-all 0.19 -> 0.08 ms per chain), measured loss at 2 (the permutation costs more than the
         # 40-/256-byte runs did); "auto" = on from 8 ranks.
@@ -555,6 +570,10 @@ class FusedDistributedFNO(nn.Module):
             self.ws["T1s"] = self.ws["T1"]
             self.ws["T1"] = torch.zeros(pl.n_T1, **bf)
         self.use_tc_bypass = (pl.S % 128 == 0 and pl.C <= 32 and os.environ.get("DFNO_TC_BYPASS", "1") != "0")
+        # round-2 dataflow: the last GEMM of every chain also applies the bypass conv (+ GELU), and the head reads
+        # the channel-major activation directly (csrc/spectral_out_sm100.cu, dpre_dw_sm100.cu, head_sm100.cu).
+        # DFNO_POINTWISE=legacy keeps round 1's separate bypass / channels-last head kernels for A/B runs.
+        self.fused_pw = os.environ.get("DFNO_POINTWISE", "fused").lower() != "legacy" and 2 * pl.KZ <= 128
 
     # ------------------------------------------------------------------ parameters
     def _seg(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -587,13 +606,17 @@ class FusedDistributedFNO(nn.Module):
         pl = self.plan
         bf = dict(device=self.device, dtype=torch.bfloat16)
         nb = self.num_blocks
-        self._saved["h"] = [torch.empty(pl.n_act, **bf) for _ in range(nb)]       # block inputs
+        # block inputs (+ the last block's output, which the head reads, in the fused pointwise dataflow)
+        self._saved["h"] = [torch.empty(pl.n_act, **bf) for _ in range(nb + (1 if self.fused_pw else 0))]
         self._saved["pre"] = [torch.empty(pl.n_act, **bf) for _ in range(nb)]     # pre-activations
         self._saved["S3"] = [torch.empty(pl.n_S3, **bf) for _ in range(nb)]       # spectra entering the mix
-        self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)                    # last block out, channels-last
         self.ws["g"] = torch.empty(pl.n_act, **bf)
-        self.ws["dhb"] = torch.empty(pl.n_act, **bf)
-        self.ws["gcl"] = torch.empty(pl.npos, pl.CP, **bf)
+        if self.fused_pw:
+            self.ws["amax"] = torch.zeros(1, device=self.device, dtype=torch.int32)
+        else:
+            self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)                # last block out, channels-last
+            self.ws["dhb"] = torch.empty(pl.n_act, **bf)
+            self.ws["gcl"] = torch.empty(pl.npos, pl.CP, **bf)
         self.grad_flat = torch.zeros(pl.n_theta, device=self.device, dtype=torch.float32)
         self.accumulate_grads = False          # True: keep adding into theta.grad across backward calls
         self._train_bufs_ready = True
@@ -604,9 +627,10 @@ class FusedDistributedFNO(nn.Module):
         pl = self.plan
         bf = dict(device=self.device, dtype=torch.bfloat16)
         self.ws["eval_h"] = [torch.empty(pl.n_act, **bf) for _ in range(2)]
-        self.ws["eval_pre"] = torch.empty(pl.n_act, **bf)
-        if "hcl" not in self._saved:
-            self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)
+        if not self.fused_pw:
+            self.ws["eval_pre"] = torch.empty(pl.n_act, **bf)
+            if "hcl" not in self._saved:
+                self._saved["hcl"] = torch.zeros(pl.npos, pl.CP, **bf)
 
     # ------------------------------------------------------------------ kernels
     def _operator(self, name: str, j0: int, n: int) -> torch.Tensor:
@@ -638,8 +662,12 @@ class FusedDistributedFNO(nn.Module):
         if st.get("barrier_after"):
             self.barrier()
 
-    def _spectral_chain(self, src, dst, block: int, adj: bool, add=None) -> None:
-        """src (engine layout) -> truncated spectrum -> channel mix -> dst (engine layout)."""
+    def _spectral_chain(self, src, dst, block: int, adj: bool, add=None, fuse: Optional[dict] = None) -> None:
+        """src (engine layout) -> truncated spectrum -> channel mix -> dst (engine layout).
+
+        ``fuse`` (round-2 dataflow): the last stage becomes ``spectral_out`` -- inverse z-DFT + bypass conv of
+        ``fuse["h"]`` with ``fuse["W"]`` (transposed in the adjoint chain) (+ GELU, pre-activation kept in
+        ``fuse["pre"]``) -- instead of a plain row-major GEMM."""
         pl = self.plan
         ws = self.ws
         s3 = self._saved["S3"][block] if (self._train_bufs_ready and not self._eval_mode) else ws["S3w"]
@@ -656,6 +684,10 @@ class FusedDistributedFNO(nn.Module):
                     self._C.spectral_mix_bwd(s3, R, bufs["S3"], bufs["S4"], gR, getattr(self, "_acc", False), pl.B, pl.C, pl.Q)
                 else:
                     self._C.spectral_mix_fwd(bufs["S3"], R, bufs["S4"], pl.B, pl.C, pl.Q)
+            elif fuse is not None and st["name"] == "iG1a":
+                self._C.spectral_out(bufs[st["src"]], fuse["h"], self.ops[st["op"] + ("_adj" if adj else "")],
+                                     fuse["W"], adj, fuse.get("pre"), dst, pl.B, pl.C, pl.X * pl.Yl * pl.T, pl.Z,
+                                     st["K"], not adj, fuse.get("pre") is not None)
             else:
                 self._gemm(st, bufs, adj, add if st["name"] == "iG1a" else None)
 
@@ -668,6 +700,18 @@ class FusedDistributedFNO(nn.Module):
         w3t = torch.zeros(32, pl.H, device=self.device, dtype=torch.bfloat16)
         w3t[:pl.C] = W3.t().to(torch.bfloat16)
         return w3, w3t
+
+    def _head_operators_cm(self):
+        """Operands of the channel-major head kernels: ``W3aug`` bf16 [H, 64] with column C = b3 (the hidden bias
+        rides through the MMA against the tile's row of ones) and ``W3^T`` as fp16 [ceil16(C+1), H]."""
+        pl = self.plan
+        W3, b3 = self._seg("linear3.W"), self._seg("linear3.b")
+        w3a = torch.zeros(pl.H, 64, device=self.device, dtype=torch.bfloat16)
+        w3a[:, :pl.C] = W3.to(torch.bfloat16)
+        w3a[:, pl.C] = b3.to(torch.bfloat16)
+        w3t = torch.zeros((pl.C + 1 + 15) // 16 * 16, pl.H, device=self.device, dtype=torch.float16)
+        w3t[:pl.C] = W3.t().to(torch.bfloat16).to(torch.float16)
+        return w3a, w3t
 
     def _wpad(self, W: torch.Tensor) -> torch.Tensor:
         """[C, C] fp32 -> zero-padded bf16 [32, 64] tcgen05 operand (rows = output index)."""
@@ -724,19 +768,32 @@ class FusedDistributedFNO(nn.Module):
         if tuple(x.shape) != expect:
             raise ValueError(f"expected local input {expect}, got {tuple(x.shape)}")
         self._eval_mode = not save
+        nb = self.num_blocks
         if save:
             self._ensure_train_buffers()
             hs, pres = self._saved["h"], self._saved["pre"]
         else:
             self._ensure_eval_buffers()
-            hs = [self.ws["eval_h"][k % 2] for k in range(self.num_blocks)]
-            pres = [self.ws["eval_pre"]] * self.num_blocks
-        hcl = self._saved["hcl"]
+            hs = [self.ws["eval_h"][k % 2] for k in range(nb + 1)]
+            pres = [self.ws.get("eval_pre")] * nb
         with _nvtx("dfno.lift"):
             C_.lift_fwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
                         self._seg("linear2.b"), hs[0], self._lift_dims())
-        for k in range(self.num_blocks):
-            last = k == self.num_blocks - 1
+        if self.fused_pw:
+            for k in range(nb):
+                with _nvtx(f"dfno.block{k}"):
+                    self._spectral_chain(hs[k], hs[k + 1], k, adj=False,
+                                         fuse=dict(h=hs[k], W=self._seg(f"blocks.{k}.linear.W"),
+                                                   pre=pres[k] if save else None))
+            with _nvtx("dfno.head"):
+                w3a, _ = self._head_operators_cm()
+                out = torch.empty(pl.B, 1, pl.X, pl.Yl, pl.Z, pl.T, device=self.device, dtype=torch.float32)
+                R, SR = self._head_row_digits()
+                C_.head_fwd(hs[nb], w3a, self._w4b4(), out, pl.B, pl.C, pl.S, R, SR)
+                return out
+        hcl = self._saved["hcl"]
+        for k in range(nb):
+            last = k == nb - 1
             with _nvtx(f"dfno.block{k}.spectral"):
                 self._spectral_chain(hs[k], pres[k], k, adj=False)
             Wb = self._seg(f"blocks.{k}.linear.W")
@@ -756,32 +813,51 @@ class FusedDistributedFNO(nn.Module):
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
         self._eval_mode = False
-        hs, pres, hcl = self._saved["h"], self._saved["pre"], self._saved["hcl"]
-        g, dhb, gcl = self.ws["g"], self.ws["dhb"], self.ws["gcl"]
+        hs, pres = self._saved["h"], self._saved["pre"]
+        g = self.ws["g"]
         if not (self.accumulate_grads and self.theta.grad is self.grad_flat):
             # spectral gradients are overwritten by the mix backward; only the small,
             # atomically accumulated segment needs clearing
             self.grad_flat[:pl.n_small].zero_()
         self._acc = bool(self.accumulate_grads and self.theta.grad is self.grad_flat)
-        with _nvtx("dfno.head.bwd"):
-            self._head_backward(hcl, dy.contiguous().float(), gcl)
-        for k in reversed(range(self.num_blocks)):
-            last = k == self.num_blocks - 1
-            Wb = self._seg(f"blocks.{k}.linear.W")
-            gW = self._seg(f"blocks.{k}.linear.W", self.grad_flat)
-            if self.use_tc_bypass:
-                # one tcgen05 kernel: dpre (over pre), dhb = W^T dpre, dW accumulated in TMEM
-                C_.bypass_bwd_tc(None if last else g, gcl if last else None, pl.CP, pres[k], hs[k],
-                                 self._wpad(Wb.t()), dhb, gW, pl.B, pl.C, pl.S)
-            else:
-                # dpre overwrites pre (same thread reads then writes each element)
-                C_.bypass_gelu_bwd(None if last else g, gcl if last else None, pl.CP, pres[k], Wb, pres[k], dhb,
-                                   pl.B, pl.C, pl.S)
-                for b in range(pl.B):
-                    sl = slice(b * pl.C * pl.S, (b + 1) * pl.C * pl.S)
-                    C_.kreduce_gemm(pres[k][sl], pl.S, pl.C, hs[k][sl], pl.S, pl.C, pl.S, gW)
-            with _nvtx(f"dfno.block{k}.spectral.bwd"):
-                self._spectral_chain(pres[k], g, k, adj=True, add=dhb)
+        gf = self.grad_flat
+        if self.fused_pw:
+            nb = self.num_blocks
+            with _nvtx("dfno.head.bwd"):
+                w3a, w3t = self._head_operators_cm()
+                R, SR = self._head_row_digits()
+                C_.head_bwd2(hs[nb], w3a, w3t, self._seg("linear4.W").view(-1), dy.contiguous().float(),
+                             self.ws["amax"], g, self._seg("linear3.W", gf), self._seg("linear3.b", gf),
+                             self._seg("linear4.W", gf).view(-1), self._seg("linear4.b", gf), pl.B, pl.C, pl.S, R, SR)
+            L = pl.X * pl.Yl * pl.T
+            for k in reversed(range(nb)):
+                with _nvtx(f"dfno.block{k}.bwd"):
+                    # dpre over pre (packed fp16 GELU'), bypass weight gradient reduced on the tensor core
+                    C_.dpre_dw(g, pres[k], hs[k], self._seg(f"blocks.{k}.linear.W", gf), pl.B, pl.C, L, pl.Z)
+                    # adjoint chain; its last GEMM adds W^T dpre (the bypass input gradient) in the same accumulator
+                    self._spectral_chain(pres[k], g, k, adj=True,
+                                         fuse=dict(h=pres[k], W=self._seg(f"blocks.{k}.linear.W")))
+        else:
+            hcl, dhb, gcl = self._saved["hcl"], self.ws["dhb"], self.ws["gcl"]
+            with _nvtx("dfno.head.bwd"):
+                self._head_backward(hcl, dy.contiguous().float(), gcl)
+            for k in reversed(range(self.num_blocks)):
+                last = k == self.num_blocks - 1
+                Wb = self._seg(f"blocks.{k}.linear.W")
+                gW = self._seg(f"blocks.{k}.linear.W", self.grad_flat)
+                if self.use_tc_bypass:
+                    # one tcgen05 kernel: dpre (over pre), dhb = W^T dpre, dW accumulated in TMEM
+                    C_.bypass_bwd_tc(None if last else g, gcl if last else None, pl.CP, pres[k], hs[k],
+                                     self._wpad(Wb.t()), dhb, gW, pl.B, pl.C, pl.S)
+                else:
+                    # dpre overwrites pre (same thread reads then writes each element)
+                    C_.bypass_gelu_bwd(None if last else g, gcl if last else None, pl.CP, pres[k], Wb, pres[k], dhb,
+                                       pl.B, pl.C, pl.S)
+                    for b in range(pl.B):
+                        sl = slice(b * pl.C * pl.S, (b + 1) * pl.C * pl.S)
+                        C_.kreduce_gemm(pres[k][sl], pl.S, pl.C, hs[k][sl], pl.S, pl.C, pl.S, gW)
+                with _nvtx(f"dfno.block{k}.spectral.bwd"):
+                    self._spectral_chain(pres[k], g, k, adj=True, add=dhb)
         C_.lift_bwd(x, self._seg("linear1.W"), self._seg("linear1.b"), self._seg("linear2.W"),
                     self._seg("linear2.b"), g, self._seg("linear1.W", self.grad_flat),
                     self._seg("linear1.b", self.grad_flat), self._seg("linear2.W", self.grad_flat),
@@ -820,7 +896,8 @@ class FusedDistributedFNO(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.R_in is not None:
             x = self.R_in(x.contiguous())
-        y = _FusedFn.apply(x, self.theta, self)
+        save = bool(torch.is_grad_enabled() and self.theta.requires_grad)
+        y = _FusedFn.apply(x, self.theta, self, save)
         if self.R_out is not None:
             y = self.R_out(y)
         return y

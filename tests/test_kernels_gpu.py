@@ -46,7 +46,7 @@ def test_lift_forward_backward(B, Cin, Tin, C, T, X, Y, Z):
     grads = [torch.zeros_like(p) for p in (W1, b1, W2, b2)]
     C_().lift_bwd(x, W1, b1, W2, b2, bf(dh).contiguous().view(-1), *grads, dims)
     for got, p in zip(grads, params):
-        assert rel(got, p.grad) < 2e-3, (got.shape, rel(got, p.grad))
+        assert rel(got, p.grad) < 5e-3, (got.shape, rel(got, p.grad))     # packed fp16 GELU' (sm100_ptx.cuh)
 
 
 # ------------------------------------------------------------------------------------------ bypass + GELU

@@ -79,14 +79,14 @@ def test_gradient_check_tool_cli():
 
 def test_bench_contract_dry_run():
     """bench.py on CPU (host-timed dry run): JSON contract keys, the reference arm's `unavailable`
-    line, and the reference-compat arm running the unmodified reference model code."""
+    line without a GPU, and the reference arm (unmodified reference model code on baseline/compat) on gloo."""
     small = ["--device", "cpu", "--grid", "16", "--nt", "8", "--width", "4", "--modes", "2", "2", "2", "2",
              "--blocks", "1", "--steps", "2", "--warmup", "3"]
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True,
                        text=True, timeout=300, cwd=ROOT)
     ref = json.loads(r.stdout.strip().splitlines()[-1])
     assert r.returncode == 0 and ref["impl"] == "reference" and ("unavailable" in ref or "value" in ref)
-    impls = ["baseline"] + (["reference-compat"] if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "dfno")) else [])
+    impls = ["baseline"] + (["reference"] if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "dfno")) else [])
     for impl in impls:
         out = _run(["bench.py", "--gpus", "2", "--impl", impl, *small])
         rec = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
