@@ -205,7 +205,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
 }
 
 // ================================================================================ backward
-constexpr int kStagesHB = 3;
+constexpr int kMaxStagesHB = 6;                 // h tiles are 8 KB: deep prefetch keeps TMA latency off the MMA warp's in-order path
 constexpr int kEpiHB = 4;                       // epilogue warps per TMEM lane quarter (one 32-column slice each)
 constexpr int kThreadsHB = 64 + 128 * kEpiHB;
 constexpr uint32_t kHD1 = 0;                    // 2 x 128 : pre-activations
@@ -214,7 +214,7 @@ constexpr uint32_t kHD3 = 352;                  // 48      : dW3 / db3 accumulat
 constexpr uint32_t kHD4 = 400;                  // 48      : dW4 accumulator (column C)
 
 struct HeadBwdParams {
-  int B, C, KR;
+  int B, C, KR, stages;
   long long S, tiles_per_b;
   const float* dout;          // fp32, public layout
   const float* amax;          // max |dout| (device scalar)
@@ -235,38 +235,39 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
   uint8_t* s_p = s_w3t + tile_bytes;                      // 2 buffers x 2 x [128 pos][64 hid] fp16
   uint8_t* s_act = s_p + 65536;
   uint8_t* s_a = s_act + 65536;                           // stages x h tile
-  uint8_t* s_hs = s_a + kStagesHB * tile_bytes;           // 2 x scaled fp16 copy of the h tile
+  uint8_t* s_hs = s_a + p.stages * tile_bytes;           // 2 x scaled fp16 copy of the h tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_hs + 2 * tile_bytes);
-  uint64_t* a_full = bars;            // [3]
-  uint64_t* a_empty = bars + 3;       // [3]
-  uint64_t* w_full = bars + 6;
-  uint64_t* d1_full = bars + 7;       // [2]
-  uint64_t* d1_empty = bars + 9;      // [2]
-  uint64_t* p_full = bars + 11;       // [2]
-  uint64_t* d2_full = bars + 13;      // [2]
-  uint64_t* all_done = bars + 15;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
-  float* s_dout = reinterpret_cast<float*>(bars + 18);     // [2][128] scaled loss gradient of the tile's rows
-  float* s_gb4 = s_dout + 256;
+  uint64_t* a_full = bars;            // [8]
+  uint64_t* a_empty = bars + 8;       // [8]
+  uint64_t* w_full = bars + 16;
+  uint64_t* d1_full = bars + 17;      // [2]
+  uint64_t* d1_empty = bars + 19;     // [2]
+  uint64_t* p_full = bars + 21;       // [2]
+  uint64_t* d2_full = bars + 23;      // [2]
+  uint64_t* all_done = bars + 25;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
+  float* s_gb4 = reinterpret_cast<float*>(bars + 28);
+  uint32_t* s_w4h = reinterpret_cast<uint32_t*>(bars + 30);   // [64] fp16x2 pairs of W4 (16-byte aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long num_tiles = p.tiles_per_b * p.B;
 
-  for (uint32_t i = threadIdx.x; i < (kStagesHB + 2) * tile_bytes / 16; i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i < (p.stages + 2) * tile_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < kStagesHB * 2 * 16; i += blockDim.x) {
+  for (uint32_t i = threadIdx.x; i < static_cast<uint32_t>(p.stages) * 2 * 16; i += blockDim.x) {
     const uint32_t hb = i >> 4, ch = i & 15;
     reinterpret_cast<uint2*>(s_a + hb * half_bytes + p.C * 128)[ch] = make_uint2(0x3F803F80u, 0x3F803F80u);
   }
   if (threadIdx.x == 0) s_gb4[0] = 0.f;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_w4h[i] = h2_bits(h2_from_f32(p.W4[2 * i], p.W4[2 * i + 1]));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmW3); tma_prefetch_desc(&tmW3T);
-    for (int s = 0; s < kStagesHB; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 4 * kEpiHB);
-      mbar_init(&p_full[i], 4 * kEpiHB); mbar_init(&d2_full[i], 1);
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 2 * kEpiHB);     // one group = 8 warps
+      mbar_init(&p_full[i], 2 * kEpiHB); mbar_init(&d2_full[i], 1);
     }
     mbar_init(all_done, 1);
     fence_barrier_init();
@@ -295,7 +296,7 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         uint8_t* st = s_a + s * tile_bytes;
         tma_load_2d(st, &tmH, &a_full[s], p0, b * p.C);
         tma_load_2d(st + half_bytes, &tmH, &a_full[s], p0 + 64, b * p.C);
-        if (++s == kStagesHB) { s = 0; ph ^= 1; }
+        if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -305,11 +306,29 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     const uint32_t idesc3 = idesc_f16(128, KR, 1, 0);                   // D3/4 += P^T-view . hs^T  (fp16)
     const int k1steps = p.KR >> 4;
     mbar_wait(w_full, 0);
-    uint32_t s = 0, ph = 0;
-    long long n = 0;
-    uint32_t prev_stage = 0;
+    const long long nt = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Two epilogue groups work on alternate tiles (buffer index = tile parity).  MMA1 runs one tile AHEAD of the
+    // reductions: MMA1(n+1) only needs the accumulator its own group drained early in tile n-1, so it is issued
+    // before part2(n) blocks on that tile's P / ACT / hs -- no group ever waits for its next pre-activations.
+    auto mma1 = [&](long long k) {
+      const int buf = static_cast<int>(k & 1);
+      const uint32_t st = static_cast<uint32_t>(k % p.stages);
+      mbar_wait(&d1_empty[buf], ((k >> 1) & 1) ^ 1);
+      mbar_wait(&a_full[st], (k / p.stages) & 1);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t abase = smem_u32(s_a + st * tile_bytes);
+        const uint32_t wbase = smem_u32(s_w3);
+        for (int ks = 0; ks < k1steps; ++ks)
+          umma_bf16_ss(tmem_base + kHD1 + buf * 128, umma_smem_desc_mn128(abase + ks * 2048, half_bytes, 1024),
+                       umma_smem_desc_k128(wbase + ks * 32), idesc1, ks > 0 ? 1u : 0u);
+        umma_commit(&d1_full[buf]);
+      }
+      __syncwarp();
+    };
     auto part2 = [&](long long mth) {
       const int pb = static_cast<int>(mth & 1);
+      const uint32_t st = static_cast<uint32_t>(mth % p.stages);
       mbar_wait(&p_full[pb], (mth >> 1) & 1);
       tcgen05_fence_after();
       if (lane == 0) {
@@ -333,140 +352,153 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
                        (mth > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&d2_full[pb]);
-        umma_commit(&a_empty[prev_stage]);
+        umma_commit(&a_empty[st]);
       }
       __syncwarp();
     };
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      const int buf = static_cast<int>(n & 1);
-      mbar_wait(&d1_empty[buf], ((n >> 1) & 1) ^ 1);
-      mbar_wait(&a_full[s], ph);
-      tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t abase = smem_u32(s_a + s * tile_bytes);
-        const uint32_t wbase = smem_u32(s_w3);
-        for (int ks = 0; ks < k1steps; ++ks)
-          umma_bf16_ss(tmem_base + kHD1 + buf * 128, umma_smem_desc_mn128(abase + ks * 2048, half_bytes, 1024),
-                       umma_smem_desc_k128(wbase + ks * 32), idesc1, ks > 0 ? 1u : 0u);
-        umma_commit(&d1_full[buf]);
-      }
-      __syncwarp();
-      if (n > 0) part2(n - 1);
-      prev_stage = s;
-      if (++s == kStagesHB) { s = 0; ph ^= 1; }
+    if (nt > 0) mma1(0);
+    for (long long n = 0; n < nt; ++n) {
+      if (n + 1 < nt) mma1(n + 1);
+      part2(n);
     }
-    if (n > 0) part2(n - 1);
     if (lane == 0) umma_commit(all_done);
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int e = (warp - 2) >> 2;               // this warp's 32-column slice of the hidden layer
-    const int m = q * 32 + lane;
-    const int tid = threadIdx.x - 64;
+    const int e = (warp - 2) >> 2;               // 0..3
+    const int g = e >> 1;                        // epilogue group: tiles of parity g (buffer set g)
+    const int sub = e & 1;                       // this warp's 64-column half of the hidden layer
+    const int m = q * 32 + lane;                 // position inside the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    __half2 w4h[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) w4h[i] = h2_from_f32(p.W4[32 * e + 2 * i], p.W4[32 * e + 2 * i + 1]);
     float acc_gb4 = 0.f;
-    long long n = 0;
-    uint32_t s = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      const int buf = static_cast<int>(n & 1), pb = buf;
+    // The 8 warps of a group own one tile at a time: warp (q, sub) handles positions 32q.. and hidden units
+    // [64 sub, 64 sub + 64); the per-position side work is split between the two warps of a quarter (hs rows of
+    // parity sub, dh channels [16 sub, 16 sub + 16)), each loading dout[m] itself (prefetched one tile ahead).
+    // The other group works on the neighbouring tile meanwhile, so TMEM / mbarrier / fence latencies of one tile
+    // overlap the GELU arithmetic of the other.
+    const uint32_t step = 2 * gridDim.x;
+    auto load_dout = [&](long long tile) -> float {
       const int b = static_cast<int>(tile / p.tiles_per_b);
       const long long pos = (tile % p.tiles_per_b) * 128 + m;
-      const bool row_ok = pos < p.S;
-      float dout = 0.f;
-      // the P / ACT / hs buffers were last read by the MMAs of tile n-2
-      if (n >= 2) mbar_wait(&d2_full[pb], ((n >> 1) - 1) & 1);
-      if (e == 0) {
-        if (row_ok) dout = p.dout[row_to_offset(p.map, static_cast<uint32_t>(b * p.S + pos))];
-        acc_gb4 += dout;
-        s_dout[pb * 128 + m] = dout * scale;
-      }
-      mbar_wait(&a_full[s], (n / kStagesHB) & 1);            // TMA image of the h tile visible to this thread
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiHB) : "memory");
-      // ---- hs: scaled fp16 copy of the tile; row C = the scaled loss gradient itself
-      if (tid < (p.C + 1) * 16) {
-        const int row = tid >> 4, j = tid & 15;
-        const uint32_t off = (j >> 3) * half_bytes + row * 128 + (((j & 7) ^ (row & 7)) << 4);
-        const float4 d0 = reinterpret_cast<const float4*>(s_dout + pb * 128 + j * 8)[0];
-        const float4 d1 = reinterpret_cast<const float4*>(s_dout + pb * 128 + j * 8)[1];
-        uint4 hv = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-        if (row < p.C) hv = *reinterpret_cast<const uint4*>(s_a + s * tile_bytes + off);
-        float2 f;
-        uint4 o;
-        f = unpack_bf16x2(hv.x); o.x = h2_bits(h2_from_f32(f.x * d0.x, f.y * d0.y));
-        f = unpack_bf16x2(hv.y); o.y = h2_bits(h2_from_f32(f.x * d0.z, f.y * d0.w));
-        f = unpack_bf16x2(hv.z); o.z = h2_bits(h2_from_f32(f.x * d1.x, f.y * d1.y));
-        f = unpack_bf16x2(hv.w); o.w = h2_bits(h2_from_f32(f.x * d1.z, f.y * d1.w));
-        *reinterpret_cast<uint4*>(s_hs + pb * tile_bytes + off) = o;
-      }
-      mbar_wait(&d1_full[buf], (n >> 1) & 1);
+      return pos < p.S ? p.dout[row_to_offset(p.map, static_cast<uint32_t>(b * p.S + pos))] : 0.f;
+    };
+    auto drain_dh = [&](long long nn, long long tile, float dout) {
+      const int b = static_cast<int>(tile / p.tiles_per_b);
+      const long long pos = (tile % p.tiles_per_b) * 128 + m;
+      if (16 * sub >= p.C) return;
+      mbar_wait(&d2_full[g], (nn >> 1) & 1);
       tcgen05_fence_after();
-      {
-        const uint32_t t1 = tmem_base + lane_addr + kHD1 + buf * 128 + 32 * e;
-        uint8_t* prow = s_p + pb * 32768 + ((32 * e) >> 6) * 16384 + m * 128;
-        uint8_t* arow = s_act + pb * 32768 + ((32 * e) >> 6) * 16384 + m * 128;
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + g * 48 + 16 * sub, v);
+      tmem_ld_wait();
+      if (pos < p.S) {
+        __nv_bfloat16* gp = p.g + (static_cast<long long>(b) * p.C + 16 * sub) * p.S + pos;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(t1 + h2 * 16, v);
-          tmem_ld_wait();
-          uint32_t pw[8], aw[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const GeluH2 vg = gelu_vg_h2(h2_from_f32(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
-            pw[i] = h2_bits(__hmul2(vg.grad, w4h[h2 * 8 + i]));
-            aw[i] = h2_bits(vg.value);
-          }
-          const uint32_t chunk = (((32 * e) & 63) >> 3) + 2 * h2;
-          const uint32_t o0 = ((chunk ^ (m & 7)) << 4), o1 = (((chunk + 1) ^ (m & 7)) << 4);
-          *reinterpret_cast<uint4*>(prow + o0) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-          *reinterpret_cast<uint4*>(prow + o1) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-          *reinterpret_cast<uint4*>(arow + o0) = make_uint4(aw[0], aw[1], aw[2], aw[3]);
-          *reinterpret_cast<uint4*>(arow + o1) = make_uint4(aw[4], aw[5], aw[6], aw[7]);
-        }
+        for (int i = 0; i < 16; ++i)
+          if (16 * sub + i < p.C) gp[static_cast<long long>(i) * p.S] = __float2bfloat16(dout * __uint_as_float(v[i]));
       }
       tcgen05_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(&d1_empty[buf]); mbar_arrive(&p_full[pb]); }
-      // ---- dh tile: only the e == 0 warps read it back
-      if (e == 0) {
-        mbar_wait(&d2_full[pb], (n >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v[16], w[16];
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + pb * 48, v);
-        tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + pb * 48 + 16, w);
+    };
+    const long long first = static_cast<long long>(blockIdx.x) + static_cast<long long>(g) * gridDim.x;
+    float dout_next = first < num_tiles ? load_dout(first) : 0.f;
+    float dout_prev = 0.f;
+    long long tile_prev = 0, n_prev = -1;
+    long long n = g;
+    for (long long tile = first; tile < num_tiles; tile += step, n += 2) {
+      const uint32_t s = static_cast<uint32_t>(n % p.stages);
+      const float dout = dout_next;
+      if (tile + step < num_tiles) dout_next = load_dout(tile + step);
+      if (sub == 0) acc_gb4 += dout;
+      mbar_wait(&d1_full[g], (n >> 1) & 1);
+      tcgen05_fence_after();
+      uint8_t* prow = s_p + g * 32768 + sub * 16384 + m * 128;
+      uint8_t* arow = s_act + g * 32768 + sub * 16384 + m * 128;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {                         // two 32-column chunks
+        uint32_t v0[16], v1[16];
+        const uint32_t t1 = tmem_base + lane_addr + kHD1 + g * 128 + 64 * sub + 32 * hh;
+        tmem_ld_32x32b_x16(t1, v0);
+        tmem_ld_32x32b_x16(t1 + 16, v1);
         tmem_ld_wait();
-        if (row_ok) {
-          __nv_bfloat16* gp = p.g + static_cast<long long>(b) * p.C * p.S + pos;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < p.C) gp[static_cast<long long>(i) * p.S] = __float2bfloat16(dout * __uint_as_float(i < 16 ? v[i & 15] : w[i & 15]));
+        if (hh == 1) {                                         // accumulator is in registers: MMA1 of this group's
+          tcgen05_fence_before();                              // next tile may overwrite it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d1_empty[g]);
         }
-        if (p.C > 32) {                       // (not reachable with the supported widths; kept for KR = 48 layouts)
-          uint32_t x[16];
-          tmem_ld_32x32b_x16(tmem_base + lane_addr + kHD2 + pb * 48 + 32, x);
-          tmem_ld_wait();
-          if (row_ok) {
-            __nv_bfloat16* gp = p.g + static_cast<long long>(b) * p.C * p.S + pos;
+        uint32_t pw[16], aw[16];
+        const uint4* wq = reinterpret_cast<const uint4*>(s_w4h + 32 * sub + 16 * hh);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (32 + i < p.C) gp[static_cast<long long>(32 + i) * p.S] = __float2bfloat16(dout * __uint_as_float(x[i]));
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const uint4 w4 = wq[i4];
+          const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = 4 * i4 + u;
+            const float x0 = __uint_as_float(i < 8 ? v0[2 * i] : v1[2 * i - 16]);
+            const float x1 = __uint_as_float(i < 8 ? v0[2 * i + 1] : v1[2 * i - 15]);
+            const GeluH2 vg = gelu_vg_h2(h2_from_f32(x0, x1));
+            pw[i] = h2_bits(__hmul2(vg.grad, h2_of_bits(ww[u])));
+            aw[i] = h2_bits(vg.value);
           }
         }
-        tcgen05_fence_before();
+        if (hh == 0) {
+          // the group's P / ACT / hs buffers were last read by the MMAs of its previous tile (n - 2)
+          if (n >= 2) mbar_wait(&d2_full[g], ((n >> 1) - 1) & 1);
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const uint32_t chunk = 4 * hh + 2 * h2;
+          const uint32_t o0 = ((chunk ^ (m & 7)) << 4), o1 = (((chunk + 1) ^ (m & 7)) << 4);
+          *reinterpret_cast<uint4*>(prow + o0) = make_uint4(pw[8 * h2 + 0], pw[8 * h2 + 1], pw[8 * h2 + 2], pw[8 * h2 + 3]);
+          *reinterpret_cast<uint4*>(prow + o1) = make_uint4(pw[8 * h2 + 4], pw[8 * h2 + 5], pw[8 * h2 + 6], pw[8 * h2 + 7]);
+          *reinterpret_cast<uint4*>(arow + o0) = make_uint4(aw[8 * h2 + 0], aw[8 * h2 + 1], aw[8 * h2 + 2], aw[8 * h2 + 3]);
+          *reinterpret_cast<uint4*>(arow + o1) = make_uint4(aw[8 * h2 + 4], aw[8 * h2 + 5], aw[8 * h2 + 6], aw[8 * h2 + 7]);
+        }
       }
-      if (++s == kStagesHB) s = 0;
+      mbar_wait(&a_full[s], (n / p.stages) & 1);              // TMA image of the h tile visible to this thread
+      {
+        // ---- hs: scaled fp16 copy of this position's column, rows c = sub, sub+2, ...; row C = the gradient itself
+        const float ds = dout * scale;
+        const uint32_t colo = (m >> 6) * half_bytes + ((m & 7) << 1);
+        const uint32_t ch = (m & 63) >> 3;
+        const uint8_t* src = s_a + s * tile_bytes;
+        uint8_t* dst = s_hs + g * tile_bytes;
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0 += 8) {
+          uint16_t hv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = sub + 2 * (k0 + k);
+            hv[k] = c < p.C ? *reinterpret_cast<const uint16_t*>(src + colo + c * 128 + ((ch ^ (c & 7)) << 4)) : 0;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = sub + 2 * (k0 + k);
+            if (c < p.C)
+              *reinterpret_cast<__half*>(dst + colo + c * 128 + ((ch ^ (c & 7)) << 4)) =
+                  __float2half_rn(__uint_as_float(static_cast<uint32_t>(hv[k]) << 16) * ds);
+          }
+        }
+        if (sub == (p.C & 1))
+          *reinterpret_cast<__half*>(dst + colo + p.C * 128 + ((ch ^ (p.C & 7)) << 4)) = __float2half_rn(ds);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (n_prev >= 0) drain_dh(n_prev, tile_prev, dout_prev);  // this group's previous tile: its MMAs retired long ago
+      dout_prev = dout;
+      tile_prev = tile;
+      n_prev = n;
     }
+    if (n_prev >= 0) drain_dh(n_prev, tile_prev, dout_prev);
+    n = n_prev + 1;                                            // > 0 iff this group processed a tile
     // ---- per-CTA flush of the weight gradients
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 16);
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 8);
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 4);
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 2);
     acc_gb4 += __shfl_xor_sync(0xffffffffu, acc_gb4, 1);
-    if (lane == 0 && e == 0) atomicAdd(s_gb4, acc_gb4);
+    if (lane == 0 && sub == 0) atomicAdd(s_gb4, acc_gb4);
     asm volatile("bar.sync 1, %0;" ::"n"(128 * kEpiHB) : "memory");
     if (n > 0 && e == 0) {
       mbar_wait(all_done, 0);
@@ -558,7 +590,7 @@ const char* head_bwd2(const void* h, const void* W3aug, const void* W3T16, const
                       long long n_dout, unsigned* amax_ws, void* g, float* gW3, float* gb3, float* gW4, float* gb4,
                       int B, int C, long long S, int nrl, const int* R, const long long* SR, int num_sms,
                       cudaStream_t stream) {
-  if (C < 1 || C > 47) return "head_bwd: 1 <= C <= 47";
+  if (C < 1 || C > 32) return "head_bwd: 1 <= C <= 32";
   if (S % 8 || S > (1ll << 31) - 256 || static_cast<long long>(B) * S > (1ll << 31) - 256) return "head_bwd: bad slab size";
   HeadBwdParams p{};
   p.B = B; p.C = C; p.KR = (C + 1 + 15) / 16 * 16; p.S = S; p.tiles_per_b = (S + 127) / 128;
@@ -578,7 +610,9 @@ const char* head_bwd2(const void* h, const void* W3aug, const void* W3T16, const
   if (cudaMemsetAsync(amax_ws, 0, 4, stream) != cudaSuccess) return "head_bwd: memset failed";
   absmax_kernel<<<num_sms * 4, 256, 0, stream>>>(dout, n_dout, amax_ws);
   const uint32_t tile_bytes = 2u * p.KR * 128;
-  const uint32_t smem_bytes = 16384 + tile_bytes + 131072 + (kStagesHB + 2) * tile_bytes + 2048 + 1024;
+  p.stages = kMaxStagesHB;
+  while (p.stages > 2 && 16384 + tile_bytes + 131072 + (p.stages + 2) * tile_bytes + 2048 + 1024 > 227 * 1024) --p.stages;
+  const uint32_t smem_bytes = 16384 + tile_bytes + 131072 + (p.stages + 2) * tile_bytes + 2048 + 1024;
   const long long tiles = p.tiles_per_b * B;
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   head_bwd2_kernel<<<grid, kThreadsHB, smem_bytes, stream>>>(tmH, tmW3, tmW3T, p);

