@@ -11,13 +11,14 @@ Synthetic fields, random-init weights.
 * ``--impl fused``     this framework's sm_100a engine (default)
 * ``--impl baseline``  the same algorithm on stock libraries (torch.fft/cuFFT + cuBLAS + NCCL
                        all_to_all/broadcast/reduce): the re-expression BASELINE.md describes
-* ``--impl reference`` the unmodified reference from baseline/_ref (needs distdl/mpi4py,
-                       which cannot be installed offline -> prints {"unavailable": ...})
-* ``--impl reference-compat``  the unmodified reference *model code* from baseline/_ref (its
-                       DistributedFNO, loss and training loop: fp32, torch.optim.Adam) on the
-                       DistDL/mpi4py import-surface layer in baseline/compat, i.e. with this
-                       repository's NCCL Repartition/Broadcast/SumReduce underneath.  Not the
-                       ``reference`` arm of the task (our communication layer is on its path).
+* ``--impl reference`` the UNMODIFIED reference from baseline/_ref through its own API (its DistributedFNO,
+                       loss and training loop: fp32, torch.optim.Adam) -- see baseline/reference_arm.py.  DistDL /
+                       mpi4py cannot be installed offline, so its imports resolve to baseline/compat, a
+                       self-contained torch.distributed (NCCL) stand-in; nothing of dfno_b200 is on that path.
+
+At N > 1 the fused arm also checks itself: the model and the global sample are functions of a seed only, rank 0
+re-runs the same steps on ONE GPU after the timed regions and the JSON line carries ``loss`` and ``loss_parity``
+(output of the freshly initialised model N ranks vs 1 rank, loss after the last step); exit code 3 on mismatch.
 
 Timing: W warm-up steps, then K steps between CUDA events bracketed by barrier +
 synchronize; max over ranks.  The per-step working set (>= 1.7 GB of activations per block)
@@ -39,7 +40,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="fused", choices=["fused", "baseline", "reference", "reference-compat"])
+    ap.add_argument("--impl", default="fused", choices=["fused", "baseline", "reference"])
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--nt", type=int, default=20)
     ap.add_argument("--width", type=int, default=20)
@@ -51,9 +52,11 @@ def parse():
                     help="P_x (default 1 1 1 GPUS 1 1); other grids run the other BASELINE configs, e.g. "
                          "--grid 256 --nt 16 --width 32 --modes 12 12 12 8 --in-channels 2 --partition 1 1 2 2 2 1")
     ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
-                    help="cpu: dry run of the baseline / reference-compat arms on gloo (host-timed; not a benchmark)")
+                    help="cpu: dry run of the baseline / reference arms on gloo (host-timed; not a benchmark)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the N-rank vs 1-rank output / loss comparison that rank 0 runs after the timed regions")
     return ap.parse_args()
 
 
@@ -115,7 +118,7 @@ class ClockSampler:
 
 def main():
     args = parse()
-    if args.impl in ("reference", "reference-compat"):
+    if args.impl == "reference":
         # the unmodified reference through its own API; nothing of dfno_b200 is imported on this path
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         import reference_arm
@@ -123,10 +126,11 @@ def main():
 
     if args.impl == "baseline":
         os.environ["DFNO_P2P_REPARTITION"] = "0"       # stock NCCL all_to_all / broadcast / reduce only
-    ref = None
+    import numpy as np
     import torch
     import torch.distributed as dist
     import dfno_b200 as d
+    from dfno_b200.parallel.decomposition import assemble_slices, shard_bounds
     from dfno_b200.utils.env import ensure_process_group
 
     N = args.gpus
@@ -148,63 +152,72 @@ def main():
 
     G, T = args.grid, args.nt
     in_shape = [args.batch, args.in_channels, G, G, G, 1]
+    out_shape = [args.batch, 1, G, G, G, T]
     grid = tuple(args.partition) if args.partition else (1, 1, 1, N, 1, 1)
     if int(torch.tensor(grid).prod()) != N:
         raise SystemExit(f"--partition {grid} does not hold --gpus {N} ranks")
     _, P_x, P_0 = d.create_standard_partitions(grid)
-    torch.manual_seed(123 + rank)
+    SEED = 1234
 
-    if args.impl == "fused":
-        net = d.DistributedFNO(P_x, in_shape, T, args.width, args.modes, num_blocks=args.blocks, device=dev,
-                               dtype=torch.bfloat16, backend="fused")
-        opt = d.FusedAdam(net, lr=1e-3)
-        in_dtype = torch.float32
-    elif ref is not None:
-        # the reference's own objects and its own loop (train_two_phase.py:78-121); fp32 is its dtype
-        _, P_ref, _ = ref.create_standard_partitions(grid)
-        net = ref.DistributedFNO(P_ref, in_shape, T, args.width, list(args.modes), num_blocks=args.blocks,
-                                 device=dev, dtype=torch.float32)
-        params = [p for p in net.parameters() if p.numel() > 0]
-        opt = torch.optim.Adam(params, lr=1e-3) if params else None
-        in_dtype = torch.float32
-    else:
-        net = d.DistributedFNO(P_x, in_shape, T, args.width, args.modes, num_blocks=args.blocks, device=dev,
-                               dtype=cdtype, backend="torch")
-        params = [p for p in net.parameters() if p.numel() > 0]
-        opt = torch.optim.Adam(params, lr=1e-3)
-        in_dtype = cdtype
-    if ref is not None:
-        crit = ref.DistributedRelativeLpLoss(P_ref).to(dev)
-    else:
-        crit = d.DistributedRelativeLpLoss(P_x, engine=net if args.impl == "fused" else None)
+    def build(P, backend):
+        if backend == "fused":
+            net_ = d.DistributedFNO(P, in_shape, T, args.width, args.modes, num_blocks=args.blocks, device=dev,
+                                    dtype=torch.bfloat16, backend="fused", init_seed=SEED)
+            return net_, d.FusedAdam(net_, lr=1e-3)
+        net_ = d.DistributedFNO(P, in_shape, T, args.width, args.modes, num_blocks=args.blocks, device=dev,
+                                dtype=cdtype, backend="torch", init_seed=SEED)
+        return net_, torch.optim.Adam([p for p in net_.parameters() if p.numel() > 0], lr=1e-3)
 
-    x_local = [int(v) for v in d.compute_distribution_info(P_x, in_shape)["shape"]]
-    y_local = [int(v) for v in d.compute_distribution_info(P_x, [args.batch, 1, G, G, G, T])["shape"]]
-    x_host = torch.randn(*x_local, dtype=in_dtype)
-    y_host = torch.randn(*y_local, dtype=torch.float32)
+    net, opt = build(P_x, "fused" if args.impl == "fused" else "torch")
+    in_dtype = torch.float32 if args.impl == "fused" else cdtype
+    crit = d.DistributedRelativeLpLoss(P_x, engine=net if args.impl == "fused" else None)
+
+    # the GLOBAL synthetic sample is a function of the seed only (every rank draws it and keeps its shard), so runs
+    # at different world sizes see the same data -- the basis of the loss-parity check below
+    gen = torch.Generator(device=dev).manual_seed(SEED)
+    x_glob = torch.randn(*in_shape, device=dev, generator=gen)
+    y_glob = torch.randn(*out_shape, device=dev, generator=gen)
+    xi, yi = d.compute_distribution_info(P_x, in_shape), d.compute_distribution_info(P_x, out_shape)
+    x_host = x_glob[tuple(xi["slice"])].to(in_dtype).contiguous().cpu()
+    y_host = y_glob[tuple(yi["slice"])].contiguous().cpu()
+    keep_global = args.impl == "fused" and N > 1 and rank == 0 and not args.no_parity
+    if not keep_global:
+        del x_glob, y_glob
     if on_gpu:
         x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
-    use_graph = args.impl == "fused" and not args.no_graph
-    tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=use_graph) if ref is None else None
+    # ---- N-rank vs 1-rank, part 1: the forward of the freshly initialised model (same seed => same global model)
+    parity = None
+    if args.impl == "fused" and N > 1 and not args.no_parity:
+        with torch.no_grad():
+            out_n = net(x_dev).float().contiguous()
+        shards = [torch.empty_like(out_n) for _ in range(N)] if rank == 0 else None
+        dist.gather(out_n, shards, dst=0)
+        if rank == 0:
+            P_1 = d.Partition([0], [1] * 6)
+            net1, opt1 = build(P_1, "fused")
+            with torch.no_grad():
+                out_1 = net1(x_glob).float()
+            out_cat = torch.empty_like(out_1)
+            for r, sh in enumerate(shards):                  # world rank r sits at grid index unravel(r, grid)
+                lo, hi = shard_bounds(out_shape, grid, [int(v) for v in np.unravel_index(r, grid)])
+                out_cat[assemble_slices(lo, hi)] = sh
+            parity = {"output_rel_err_vs_1rank_initial": float((out_cat - out_1).norm() / out_1.norm().clamp_min(1e-30))}
+            del out_cat, out_1, shards
+        del out_n
 
-    def ref_step(xd, yd):
-        if opt is not None:
-            opt.zero_grad()
-        loss = crit(net(xd), yd)
-        loss.backward()
-        if opt is not None:
-            opt.step()
-        return loss
+    use_graph = args.impl == "fused" and not args.no_graph
+    tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=use_graph)
+    steps_taken = [0]
 
     def step_device():
-        return tr.step_on_device(x_dev, y_dev) if tr is not None else ref_step(x_dev, y_dev)
+        steps_taken[0] += 1
+        return tr.step_on_device(x_dev, y_dev)
 
     def step_e2e():
-        if tr is not None:
-            return tr.step(x_host, y_host, next_batch=(x_host, y_host))
-        return float(ref_step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)))
+        steps_taken[0] += 1
+        return tr.step(x_host, y_host, next_batch=(x_host, y_host))
 
     def sync_all():
         if N > 1:
@@ -220,8 +233,9 @@ def main():
         else:
             import time
             t0 = time.perf_counter()
+        last = None
         for _ in range(steps):
-            fn()
+            last = fn()
         if on_gpu:
             e.record()
         sync_all()
@@ -229,7 +243,7 @@ def main():
         ms = torch.tensor([elapsed], device=dev, dtype=torch.float64)
         if N > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), last
 
     sampler = ClockSampler(local)
     if rank == 0 and on_gpu:
@@ -238,32 +252,50 @@ def main():
         step_device()
     counter = getattr(net, "_C", None)
     c0 = counter.count if hasattr(counter, "count") else 0
-    total_ms = timed(step_device, args.steps)
+    total_ms, last_loss = timed(step_device, args.steps)
     launches = (counter.count - c0) if hasattr(counter, "count") else 0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = total_ms / args.steps
     value = args.batch * 1000.0 / ms_step
+    loss_value = float(last_loss)
 
     # ---- end to end through the public Trainer API: pinned host batch in, loss out
     e2e = None
     if not args.no_e2e:
         for _ in range(3):
             step_e2e()
-        e2e_ms = timed(step_e2e, args.steps)
-        nbytes = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
+        e2e_ms, last_loss = timed(step_e2e, args.steps)
+        loss_value = float(last_loss)
         e2e = {"value": args.batch * 1000.0 / (e2e_ms / args.steps), "unit": "samples/s",
-               "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": tr.h2d_bytes if tr is not None else nbytes,
-               "d2h_bytes_per_step": tr.d2h_bytes if tr is not None else 4,
-               "cuda_graph": bool(tr is not None and tr._graph is not None),
-               "how": ("Trainer.step(): pinned host batch -> async H2D (double buffered) -> fwd+loss+bwd+Adam -> loss D2H"
-                       if tr is not None else "reference loop: pinned host batch -> H2D -> fwd+loss+bwd+Adam -> loss.item()")}
+               "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": tr.h2d_bytes, "d2h_bytes_per_step": tr.d2h_bytes,
+               "cuda_graph": bool(tr._graph is not None),
+               "how": "Trainer.step(): pinned host batch -> async H2D (double buffered) -> fwd+loss+bwd+Adam -> loss D2H"}
+
+    # ---- N-rank vs 1-rank, part 2: rank 0 repeats the same number of optimisation steps on ONE GPU with the same
+    # model / data and compares the loss after the last step (not timed; the other ranks wait at the barrier)
+    if parity is not None:
+        crit1 = d.DistributedRelativeLpLoss(P_1)
+        x1, y1 = x_glob.to(in_dtype), y_glob
+        l1 = None
+        for _ in range(steps_taken[0]):
+            opt1.zero_grad()
+            l1 = crit1(net1(x1), y1)
+            l1.backward()
+            opt1.step()
+        l1 = float(l1)
+        parity.update({"steps": steps_taken[0], "loss_n_ranks": loss_value, "loss_1_rank": l1,
+                       "abs_diff": abs(loss_value - l1)})
+        parity["ok"] = bool(parity["abs_diff"] < 2e-3 * max(1.0, abs(l1)) and
+                            parity["output_rel_err_vs_1rank_initial"] < 2e-2)
+        if not parity["ok"]:
+            print(f"[bench] LOSS PARITY FAILED: {parity}", file=sys.stderr)
 
     if rank == 0:
         out = {
             "metric": "3D Navier-Stokes FNO training step (fwd+loss+bwd+Adam) samples/sec, whole job, device-timed, max over ranks",
             "value": value, "unit": "samples/s", "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "fp32" if (ref is not None or not on_gpu) else "bf16", "data": "synthetic (random fields, random-init weights)", "impl": args.impl,
+            "dtype": "bf16" if on_gpu else "fp32", "data": "synthetic (random fields, random-init weights)", "impl": args.impl,
             "config": {"model": f"FNO3d+t {G}^3x{T}t width {args.width} modes {tuple(args.modes)} blocks {args.blocks}",
                        "global_batch": args.batch, "seq_len": G * G * G * T,
                        "parallelism": (f"y-pencil 1x{N} (model parallel: field over y, spectral weights over kz)"
@@ -271,13 +303,14 @@ def main():
                        "l2": "per-step working set (>=0.2 GB/rank/block activations) exceeds the 126 MB L2; no flush needed",
                        "step": "forward + DistributedRelativeLpLoss + backward + Adam"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "cuda_graph": bool(tr is not None and tr._graph is not None),
+            "cuda_graph": bool(tr._graph is not None), "loss": loss_value, "loss_parity": parity,
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30 if on_gpu else None,
         }
         print(json.dumps(out))
     if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 0 if (parity is None or parity.get("ok", True)) else 3
 
 
 if __name__ == "__main__":

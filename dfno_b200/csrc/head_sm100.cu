@@ -482,10 +482,12 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
         if (sub == (p.C & 1))
           *reinterpret_cast<__half*>(dst + colo + p.C * 128 + ((ch ^ (p.C & 7)) << 4)) = __float2half_rn(ds);
       }
+      // this group's previous tile (its MMAs retired long ago).  Must precede the p_full arrival: the reductions of
+      // THIS tile write the same D2 buffer as soon as all eight warps have arrived.
+      if (n_prev >= 0) drain_dh(n_prev, tile_prev, dout_prev);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
-      if (n_prev >= 0) drain_dh(n_prev, tile_prev, dout_prev);  // this group's previous tile: its MMAs retired long ago
       dout_prev = dout;
       tile_prev = tile;
       n_prev = n;

@@ -133,7 +133,9 @@ class DistributedFieldDataset(Dataset):
     def _cache_file(self, i: int) -> Optional[str]:
         if self.savepath is None:
             return None
-        return os.path.join(self.savepath, f"{self.filename}_{i:04d}_{max(self.P_feat.rank, 0):04d}.npz")
+        if not self.P_feat.active:      # a rank outside the feature partition owns nothing: no cache file
+            return None
+        return os.path.join(self.savepath, f"{self.filename}_{i:04d}_{self.P_feat.rank:04d}.npz")
 
     def _normalise(self, a: np.ndarray) -> np.ndarray:
         """Global min/max scaling to [0, 1] (MIN/MAX all-reduce over the partition)."""

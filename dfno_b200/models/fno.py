@@ -144,8 +144,19 @@ class DistributedFNOBlock(nn.Module):
                 self.slices.append((slice(None), slice(None)) + tuple(slice(a, b) for a, b in box))
 
         # data-parallel replicas (batch axis of P_y partitioned) share each weight shard:
-        # their gradients are summed in the backward
+        # their gradients are summed in the backward ...
         self.replica_group, self.replica_ranks = self.P_y.axis_group([0])
+        # ... so they must also START from the same values: every replica drew its shard from its own RNG
+        # stream, the first rank of the replica set wins (without this the replicas train different models
+        # forever while applying identical gradients)
+        if self.replica_group is not None:
+            import torch.distributed as dist
+            with torch.no_grad():
+                for w in self.weights:
+                    buf = torch.view_as_real(w.data) if w.is_complex() else w.data
+                    buf = buf.contiguous()
+                    dist.broadcast(buf, src=self.replica_ranks[0], group=self.replica_group)
+                    (torch.view_as_real(w.data) if w.is_complex() else w.data).copy_(buf)
 
         letters = alphabet(P_x.dim, as_array=True)
         xs, ws, ys = list(letters), list(letters), list(letters)
@@ -238,8 +249,11 @@ class DistributedFNO(nn.Module):
 
     def __init__(self, P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
                  modes: Sequence[int], num_blocks: int = 4, device=torch.device("cpu"),
-                 dtype=torch.float32, plan: str = "reference", backend: str = "auto"):
+                 dtype=torch.float32, plan: str = "reference", backend: str = "auto",
+                 init_seed: Optional[int] = None):
         super().__init__()
+        if init_seed is not None:       # reproducible draw (per rank; the fused engine's is partition independent)
+            torch.manual_seed(int(init_seed) + 7919 * max(int(P_x.rank), 0))
         self.P_x = P_x
         self.in_shape = [int(s) for s in in_shape]
         self.out_timesteps, self.width = int(out_timesteps), int(width)

@@ -54,16 +54,28 @@ HEAD_HIDDEN = 128
 # eligibility
 # =====================================================================================
 
+def _as_6d(grid: Sequence[int], in_shape: Sequence[int], modes: Sequence[int]):
+    """The engine computes on 6-D ``[B, C, X, Y, Z, T]`` tensors.  A 2-D + time problem ``[B, C, X', Y', T]`` (the
+    reference's Navier-Stokes trainer, ``experiment_navier_stokes.py:22,30``) is the same thing with a singleton
+    leading spatial axis -- ``[B, C, 1, X', Y', T]`` is a free view -- whose (identity) x-transform the plan skips.
+    Returns ``(grid6, in_shape6, modes6, five_d)``; lengths other than 5 / 6 give ``None``."""
+    g, sh, m = [int(v) for v in grid], [int(v) for v in in_shape], [int(v) for v in modes]
+    if len(g) == 6 and len(sh) == 6 and len(m) == 4:
+        return g, sh, m, False
+    if len(g) == 5 and len(sh) == 5 and len(m) == 3:
+        return [g[0], g[1], 1, g[2], g[3], g[4]], [sh[0], sh[1], 1, sh[2], sh[3], sh[4]], [0, m[0], m[1], m[2]], True
+    return None
+
+
 def _pencil_axis(grid: Sequence[int]) -> Optional[int]:
-    """Return the partitioned axis if ``grid`` is a supported 1 x P pencil, else None."""
+    """Return the partitioned axis if ``grid`` (5-D or 6-D) is a supported 1 x P pencil, else None."""
     g = [int(v) for v in grid]
-    if len(g) != 6:
+    if len(g) not in (5, 6):
         return None
+    pa = len(g) - 3                       # the engine's y axis: public Y (6-D) / public X (5-D)
     parted = [i for i, v in enumerate(g) if v > 1]
-    if not parted:
-        return 3
-    if parted == [3]:
-        return 3
+    if not parted or parted == [pa]:
+        return pa
     return None
 
 
@@ -73,7 +85,10 @@ def fold_onto_pencil(P_x: Partition, in_shape: Sequence[int], out_timesteps: int
     if _pencil_axis(P_x.shape) is not None:
         return P_x, None, None
     from ..parallel.primitives import Repartition
-    P_work = P_x.create_cartesian_topology_partition([1, 1, 1, int(np.prod(P_x.shape)), 1, 1])
+    nd = int(P_x.dim)
+    work = [1] * nd
+    work[nd - 3] = int(np.prod(P_x.shape))
+    P_work = P_x.create_cartesian_topology_partition(work)
     out_shape = [int(in_shape[0]), 1, *[int(v) for v in in_shape[2:-1]], int(out_timesteps)]
     return P_work, Repartition(P_x, P_work, [int(v) for v in in_shape]), Repartition(P_work, P_x, out_shape)
 
@@ -86,37 +101,37 @@ def supports(P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width:
     split (e.g. BASELINE config 3's ``(1,1,2,2,2,1)`` or config 4's 8-way time partition) is served
     by re-sharding the (small) network input onto that pencil once, running the engine there and
     re-sharding the single-channel output back -- instead of the reference's two full-resolution
-    re-shards R1/R4 per Fourier layer (``/root/reference/dfno/dfno.py:247,288``)."""
-    if P_x.dim != 6:
-        return False, "fused engine covers 3-D + time fields (6-D tensors)"
-    grid = [int(v) for v in P_x.shape]
+    re-shards R1/R4 per Fourier layer (``/root/reference/dfno/dfno.py:247,288``).  5-D (2-D + time)
+    problems run as 6-D ones with a singleton x axis (:func:`_as_6d`)."""
+    six = _as_6d(P_x.shape, in_shape, modes)
+    if six is None:
+        return False, "fused engine covers 2-D + time and 3-D + time fields (5-D / 6-D tensors)"
+    grid, shape6, modes6, _ = six
     if grid[0] != 1:
         return False, "batch-partitioned P_x (data parallel) runs on the portable backend"
     P = int(np.prod(grid))
-    B, Cin, X, Y, Z, Tin = [int(s) for s in in_shape]
+    B, Cin, X, Y, Z, Tin = shape6
     T = int(out_timesteps)
-    mx, my, mz, mt = [int(m) for m in modes]
+    mx, my, mz, mt = modes6
     if width not in SUPPORTED_WIDTHS:
         return False, f"width {width} not in {SUPPORTED_WIDTHS}"
     if P > 8:
         return False, "at most 8 peers (one NVSwitch box)"
     if Y % P or (2 * mz) % P:
         return False, "Y and 2*modes_z must divide evenly over the pencil"
-    if Cin > 4 or Cin * Tin > 32:
-        return False, "lift kernel covers Cin <= 4 and Cin*Tin <= 32"
-    # T % 4 != 0 (e.g. the reference's two-phase run, T = 30) is handled by a padded t pitch in Z1
-    # (EnginePlan.Tp); replayed in float64 by tests/test_engine_plan.py but not yet run on a B200,
-    # hence opt-in for now.
-    t_ok = T % 4 == 0 or (T % 2 == 0 and os.environ.get("DFNO_FUSED_PADDED_T", "0") != "0")
-    if Z % 8 or not t_ok or Y % 4 or X % 4 or mx % 2 or my % 2 or mz % 2:
-        return False, "extents must satisfy Z%8 = T%4 = X%4 = Y%4 = 0 and even modes (TMA pitch alignment)"
-    if 2 * mx > X or 2 * my > Y or 2 * mz > Z or mt > T // 2 + 1:
+    if Cin > 4 or Tin > 64:
+        return False, "lift kernel covers Cin <= 4 and Tin <= 64"
+    # T % 4 != 0 (e.g. the reference's two-phase run and in-module demo, T = 30) uses a padded t pitch in Z1
+    # (EnginePlan.Tp); validated on a B200 in round 2 (tests/test_fused_gpu.py)
+    if Z % 8 or T % 2 or Y % 4 or (X % 4 and X != 1) or (mx % 2 and X != 1) or my % 2 or mz % 2:
+        return False, "extents must satisfy Z%8 = T%2 = X%4 = Y%4 = 0 and even modes (TMA pitch alignment)"
+    if (X != 1 and 2 * mx > X) or 2 * my > Y or 2 * mz > Z or mt > T // 2 + 1:
         return False, "mode counts exceed the axes"
     if max(Z, 2 * T) > 256 or max(2 * X, 2 * Y) > 512:
         return False, "transformed axes: Z <= 256, T <= 128, X, Y <= 256 samples"
     if B * width * X * (Y // P) * Z * T >= 2 ** 31:
         return False, "per-rank activation must stay below 2^31 elements"
-    pl = EnginePlan(B, Cin, Tin, width, T, X, Y, Z, modes, world=P, rank=0)
+    pl = EnginePlan(B, Cin, Tin, width, T, X, Y, Z, modes6, world=P, rank=0)
     pl.finish(4)
     need = pl.memory_bytes(train=True)["total"]
     if need > HBM_BUDGET:
@@ -172,7 +187,8 @@ class EnginePlan:
         self.max_n = MAX_N                                 # widest operator one GEMM launch keeps resident
         self.Yl = Y // world
         self.y_off = rank * self.Yl
-        self.KX, self.KY, self.KZ = 2 * self.mx, 2 * self.my, 2 * self.mz
+        self.has_x = X > 1                                 # X == 1: 2-D + time problem, no x transform (see _as_6d)
+        self.KX, self.KY, self.KZ = (2 * self.mx if self.has_x else 1), 2 * self.my, 2 * self.mz
         self.kzl = self.KZ // world
         self.kz_off = rank * self.kzl
         self.mtp = (self.mt + 3) // 4 * 4
@@ -266,23 +282,29 @@ class EnginePlan:
             # S1s[a=(bc,kzl,kt), r_src, x, y_loc] -> S1[a, x, (r_src, y_loc)]   (32-bit words = complex pairs)
             st.append(dict(name="permS1", src="S1s", dst="S1", size=[Yl, P, X, BC * m_loc],
                            sstr=[1, X * Yl, Yl, P * X * Yl], dstr=[1, Yl, Y, X * Y]))
-        st.append(dict(name="G2", src="S1", dst="S2", M=BC * m_loc * X, K=2 * Y, lda=2 * Y, N=2 * KY, op="G2",
+        # X == 1: S2[bc, kz, kt, ky, x=1, ri] already is the row-major S3 layout and T2 the S4 layout, so the x stages vanish
+        st.append(dict(name="G2", src="S1", dst="S2" if self.has_x else "S3", M=BC * m_loc * X, K=2 * Y, lda=2 * Y,
+                       N=2 * KY, op="G2",
                        scatter=ScatterSpec(rows=[(X, 2), (BC * m_loc, KY * X * 2)], cols=(KY, X * 2, 0))))
-        st.append(dict(name="G3", src="S2", dst="S3", M=BC * m_loc * KY, K=2 * X, lda=2 * X, N=2 * KX, op="G3",
-                       ldc=2 * KX))
+        if self.has_x:
+            st.append(dict(name="G3", src="S2", dst="S3", M=BC * m_loc * KY, K=2 * X, lda=2 * X, N=2 * KX, op="G3",
+                           ldc=2 * KX))
         st.append(dict(name="mix"))
-        st.append(dict(name="iG3", src="S4", dst="T2", M=BC * m_loc * KY, K=2 * KX, lda=2 * KX, N=2 * X, op="iG3",
-                       scatter=ScatterSpec(rows=[(KY, 2), (m_loc, KY * 2), (BC, X * m_loc * KY * 2)],
-                                           cols=(X, m_loc * KY * 2, 0))))
+        if self.has_x:
+            st.append(dict(name="iG3", src="S4", dst="T2", M=BC * m_loc * KY, K=2 * KX, lda=2 * KX, N=2 * X, op="iG3",
+                           scatter=ScatterSpec(rows=[(KY, 2), (m_loc, KY * 2), (BC, X * m_loc * KY * 2)],
+                                               cols=(X, m_loc * KY * 2, 0))))
         if not staged_r3:
-            st.append(dict(name="iG2", src="T2", dst="T1", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
+            st.append(dict(name="iG2", src="T2" if self.has_x else "S4", dst="T1", M=BC * X * m_loc, K=2 * KY,
+                           lda=2 * KY, N=2 * Y, op="iG2",
                            scatter=ScatterSpec(rows=[(mt, 2), (kzl, mtp * 2), (X, Yl * KZ * mtp * 2),
                                                      (BC, X * Yl * KZ * mtp * 2)],
                                                cols=(Yl, KZ * mtp * 2, 0), peer=("col", Yl),
                                                base_off=self.kz_off * mtp * 2),
                            peer_dst=True, barrier_after=True))
         else:
-            st.append(dict(name="iG2", src="T2", dst="T1s", M=BC * X * m_loc, K=2 * KY, lda=2 * KY, N=2 * Y, op="iG2",
+            st.append(dict(name="iG2", src="T2" if self.has_x else "S4", dst="T1s", M=BC * X * m_loc, K=2 * KY,
+                           lda=2 * KY, N=2 * Y, op="iG2",
                            scatter=ScatterSpec(rows=[(mt, 2), (kzl, mt * 2), (X, m_loc * 2),
                                                      (BC, P * Yl * X * m_loc * 2)],
                                                cols=(Yl, X * m_loc * 2, 0), peer=("col", Yl),
@@ -319,7 +341,7 @@ class EnginePlan:
                 continue
         raise ValueError(f"stage {st['name']}: no column split of {npairs} pairs fits {self.max_n}")
 
-    def memory_bytes(self, train: bool = True, staged: Optional[bool] = None) -> Dict[str, int]:
+    def memory_bytes(self, train: bool = True, staged: Optional[bool] = None, legacy: bool = False) -> Dict[str, int]:
         """Per-rank device memory of the engine for this plan, by category (bytes).  Mirrors the
         allocations of :class:`FusedDistributedFNO` (``__init__``, ``_ensure_train_buffers``,
         ``_ensure_eval_buffers``) and :class:`FusedAdam`; used to size shards for the 180 GB of a B200
@@ -337,18 +359,22 @@ class EnginePlan:
                         if self.world > 1 else 0) + (self.n_small * f32 if self.world > 1 else 0),
             "input_output": self.B * self.S // self.T * self.Cin * self.Tin * f32 + self.B * self.S * f32,
         }
-        if train:
+        if train and legacy:            # round-1 dataflow (DFNO_POINTWISE=legacy): channels-last head, separate bypass
             out["saved_activations"] = (2 * nb * self.n_act + nb * self.n_S3 + cl) * bf
             out["backward_workspaces"] = (2 * self.n_act + cl) * bf
+        elif train:                     # block inputs + last output, pre-activations, spectra entering the mix
+            out["saved_activations"] = ((2 * nb + 1) * self.n_act + nb * self.n_S3) * bf
+            out["backward_workspaces"] = self.n_act * bf
+        if train:
             out["gradients"] = self.n_theta * f32
             out["adam_moments"] = 2 * self.n_theta * f32
         else:
-            out["eval_activations"] = (3 * self.n_act + cl) * bf
+            out["eval_activations"] = ((3 * self.n_act + cl) if legacy else 2 * self.n_act) * bf
         out["total"] = sum(out.values())
         return out
 
     def cost_model(self, hbm_gbs: float = 6491.8, nvlink_gbs: float = 770.0,
-                   staged: Optional[bool] = None) -> Dict[str, object]:
+                   staged: Optional[bool] = None, legacy: bool = False) -> Dict[str, object]:
         """Bytes every kernel of one training step must move (per rank) and the resulting floors.
 
         Pure bookkeeping of the dataflow in :class:`FusedDistributedFNO` -- each stage reads its input
@@ -371,18 +397,27 @@ class EnginePlan:
         W = self.C * self.C * self.Q * 2 * f32                         # one block's spectral shard
         off = (P - 1) / P if P > 1 else 0.0
         chain = [("G1a", act + Z1, 0), ("G1b", Z1 + S1, S1 * off), ("G2", S1 + S2, 0), ("G3", S2 + S3, 0),
-                 ("iG3", S3 + T2, 0), ("iG2", T2 + T1, T1 * off), ("iG1b", T1 + U, 0), ("iG1a", U + act, 0)]
+                 ("iG3", S3 + T2, 0), ("iG2", T2 + T1, T1 * off), ("iG1b", T1 + U, 0)]
+        if not self.has_x:
+            chain = [c for c in chain if c[0] not in ("G3", "iG3")]
+        if legacy:
+            chain.append(("iG1a", U + act, 0))
         if P > 1 and staged in (True, "r2"):
             chain.append(("permS1", 2 * S1, 0))
         if P > 1 and staged in (True, "r3"):
             chain.append(("permT1", 2 * T1, 0))
         st = [(n, 2 * nb, b, l) for n, b, l in chain]                  # forward + adjoint chain per block
-        st += [("iG1a add (bwd)", nb, act, 0),
-               ("spectral_mix fwd", nb, 2 * S3 + W, 0), ("spectral_mix bwd", nb, 3 * S3 + 2 * W, 0),
-               ("bypass fwd", nb, 4 * act, 0), ("bypass bwd", nb, 5 * act, 0),
-               ("lift fwd", 1, act, 0), ("lift bwd", 1, act, 0),
-               ("head fwd", 1, cl + self.npos * f32, 0), ("head bwd", 1, 2 * cl + self.npos * f32, 0),
-               ("adam", 1, 7 * self.n_theta * f32, 0)]
+        st += [("spectral_mix fwd", nb, 2 * S3 + W, 0), ("spectral_mix bwd", nb, 3 * S3 + 2 * W, 0),
+               ("lift fwd", 1, act, 0), ("lift bwd", 1, act, 0), ("adam", 1, 7 * self.n_theta * f32, 0)]
+        if legacy:
+            st += [("iG1a add (bwd)", nb, act, 0), ("bypass fwd", nb, 4 * act, 0), ("bypass bwd", nb, 5 * act, 0),
+                   ("head fwd", 1, cl + self.npos * f32, 0), ("head bwd", 1, 2 * cl + self.npos * f32, 0)]
+        else:
+            # the chain's last GEMM also applies the bypass conv (+ GELU): reads U and the block input, writes the
+            # pre-activation and the output (forward) / reads U and dpre, writes the input gradient (adjoint)
+            st += [("spectral_out fwd", nb, U + 3 * act, 0), ("spectral_out adj", nb, U + 2 * act, 0),
+                   ("dpre_dw", nb, 4 * act, 0),
+                   ("head fwd", 1, act + self.npos * f32, 0), ("head bwd", 1, 2 * act + 2 * self.npos * f32, 0)]
         hbm = sum(c * b for _, c, b, _ in st)
         link = sum(c * l for _, c, _, l in st)
         return {"stages": st, "hbm_bytes": hbm, "nvlink_bytes": link,
@@ -394,12 +429,13 @@ class EnginePlan:
         X, Y, Z, T = self.X, self.Y, self.Z, self.T
         f = {
             "G1a": OPS.fwd_real_to_complex(Z, self.mz), "G1b": OPS.fwd_complex(T, self.mt, False),
-            "G2": OPS.fwd_complex(Y, self.my), "G3": OPS.fwd_complex(X, self.mx),
-            "iG3": OPS.inv_complex(X, self.mx), "iG2": OPS.inv_complex(Y, self.my),
+            "G2": OPS.fwd_complex(Y, self.my), "iG2": OPS.inv_complex(Y, self.my),
             "iG1b": OPS.inv_complex_hermitian(T, self.mt), "iG1a": OPS.inv_complex_to_real(Z, self.mz),
         }
-        mirror = {"G1a": "iG1a", "G1b": "iG1b", "G2": "iG2", "G3": "iG3",
-                  "iG3": "G3", "iG2": "G2", "iG1b": "G1b", "iG1a": "G1a"}
+        mirror = {"G1a": "iG1a", "G1b": "iG1b", "G2": "iG2", "iG2": "G2", "iG1b": "G1b", "iG1a": "G1a"}
+        if self.has_x:
+            f["G3"], f["iG3"] = OPS.fwd_complex(X, self.mx), OPS.inv_complex(X, self.mx)
+            mirror.update({"G3": "iG3", "iG3": "G3"})
         out = dict(f)
         for slot, src in mirror.items():       # the adjoint chain's stage in slot X is adj(mirror(X))
             out[slot + "_adj"] = f[src].t().contiguous()
@@ -489,7 +525,7 @@ class FusedDistributedFNO(nn.Module):
     def __init__(self, P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
                  modes: Sequence[int], num_blocks: int = 4, device=torch.device("cuda"),
                  dtype=torch.bfloat16, plan: Optional[str] = None, backend: str = "fused",
-                 use_p2p: Optional[bool] = None):
+                 use_p2p: Optional[bool] = None, init_seed: Optional[int] = None):
         super().__init__()
         ok, why = supports(P_x, in_shape, out_timesteps, width, modes)
         if not ok:
@@ -508,15 +544,18 @@ class FusedDistributedFNO(nn.Module):
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = torch.bfloat16
         self.block_in_shape = [self.in_shape[0], self.width, *self.in_shape[2:-1], self.out_timesteps]
-        B, Cin, X, Y, Z, Tin = self.in_shape
+        # 2-D + time problems run as 3-D + time with a singleton x axis (free views at entry / exit)
+        _, shape6, modes6, self.five_d = _as_6d(P_x.shape, self.in_shape, self.modes)
+        B, Cin, X, Y, Z, Tin = shape6
         # work partition: the y-pencil the engine computes on.  A differently shaped P_x is folded
         # onto it once at the network's entry / exit (see supports()).
         self.P_outer = P_x
         self.P_work, self.R_in, self.R_out = fold_onto_pencil(P_x, self.in_shape, self.out_timesteps)
         P_x = self.P_work
-        self.world = int(P_x.shape[3]) if P_x.active else 1
-        self.rank = int(P_x.index[3]) if P_x.active else 0
-        self.plan = EnginePlan(B, Cin, Tin, self.width, self.out_timesteps, X, Y, Z, self.modes,
+        pa = P_x.dim - 3                             # the pencil axis of the work partition
+        self.world = int(P_x.shape[pa]) if P_x.active else 1
+        self.rank = int(P_x.index[pa]) if P_x.active else 0
+        self.plan = EnginePlan(B, Cin, Tin, self.width, self.out_timesteps, X, Y, Z, modes6,
                                self.world, self.rank)
         self.plan.finish(self.num_blocks)
         pl = self.plan
@@ -525,7 +564,7 @@ class FusedDistributedFNO(nn.Module):
         # ---- parameters: one flat fp32 buffer
         theta = torch.zeros(pl.n_theta, device=self.device, dtype=torch.float32)
         self.theta = nn.Parameter(theta)
-        self._init_parameters()
+        self._init_parameters(init_seed)
 
         # ---- operators (bf16, padded) for the forward and the adjoint chain
         self._ops_f64 = pl.operators()
@@ -581,18 +620,40 @@ class FusedDistributedFNO(nn.Module):
         base = self.theta.data if base is None else base
         return base[off:off + int(np.prod(shape))].view(shape)
 
-    def _init_parameters(self) -> None:
+    def _init_parameters(self, seed: Optional[int] = None) -> None:
+        """Reference initialisation (``/root/reference/dfno/dfno.py:35-36,114-117,160``): Kaiming-uniform pointwise
+        weights, zero biases, ``U[0,1)/C^2`` spectral weights.  With ``seed`` the draw is *partition independent*:
+        pointwise weights come from one generator seeded identically on every rank and every retained ``kz`` slab
+        of every block from its own generator seeded by its GLOBAL index, so 1, 2, 4 and 8 ranks build the same
+        model (``bench.py`` uses this to check an N-rank run against a 1-rank run)."""
         pl = self.plan
         with torch.no_grad():
+            gen = None
+            if seed is not None:
+                gen = torch.Generator(device=self.device)
+                gen.manual_seed(int(seed))
             for name, (off, shape) in pl.segments.items():
                 t = self._seg(name)
                 if name.endswith(".spectral"):
-                    t.copy_(torch.rand(shape, device=self.device) / (self.width * self.width))
+                    if seed is None:
+                        t.copy_(torch.rand(shape, device=self.device) / (self.width * self.width))
+                    else:
+                        k = int(name.split(".")[1])
+                        slab = t.view(pl.C, pl.C, pl.kzl, pl.mt * pl.KY * pl.KX, 2)
+                        g2 = torch.Generator(device=self.device)
+                        for j in range(pl.kzl):
+                            g2.manual_seed(int(seed) * 1000003 + k * 4099 + pl.kz_off + j + 1)
+                            slab[:, :, j] = torch.rand(pl.C, pl.C, slab.shape[3], 2, device=self.device,
+                                                       generator=g2) / (self.width * self.width)
                 elif name.endswith(".W"):
-                    nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+                    if seed is None:
+                        nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+                    else:                                   # kaiming_uniform_(a=sqrt(5)): U(-1/sqrt(fan_in), +)
+                        bound = 1.0 / math.sqrt(shape[1])
+                        t.copy_((torch.rand(shape, device=self.device, generator=gen) * 2 - 1) * bound)
                 else:
                     t.zero_()
-            if self.world > 1:            # replicated pointwise weights: everyone takes rank 0's draw
+            if self.world > 1 and seed is None:   # replicated pointwise weights: everyone takes rank 0's draw
                 small = self.theta.data[:pl.n_small]
                 dist.broadcast(small, src=self.P_work.world_ranks[0], group=self.P_work.group)
 
@@ -765,8 +826,11 @@ class FusedDistributedFNO(nn.Module):
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
         expect = (pl.B, pl.Cin, pl.X, pl.Yl, pl.Z, pl.Tin)
+        if self.five_d and x.dim() == 5:
+            x = x.unsqueeze(2)
         if tuple(x.shape) != expect:
-            raise ValueError(f"expected local input {expect}, got {tuple(x.shape)}")
+            raise ValueError(f"expected local input {expect[:2] + expect[3:] if self.five_d else expect}, "
+                             f"got {tuple(x.shape)}")
         self._eval_mode = not save
         nb = self.num_blocks
         if save:
@@ -790,7 +854,7 @@ class FusedDistributedFNO(nn.Module):
                 out = torch.empty(pl.B, 1, pl.X, pl.Yl, pl.Z, pl.T, device=self.device, dtype=torch.float32)
                 R, SR = self._head_row_digits()
                 C_.head_fwd(hs[nb], w3a, self._w4b4(), out, pl.B, pl.C, pl.S, R, SR)
-                return out
+                return out.squeeze(2) if self.five_d else out
         hcl = self._saved["hcl"]
         for k in range(nb):
             last = k == nb - 1
@@ -805,13 +869,16 @@ class FusedDistributedFNO(nn.Module):
                     C_.bypass_gelu_fwd(hs[k], pres[k], Wb, None if last else hs[k + 1], hcl if last else None,
                                        pl.CP, pl.B, pl.C, pl.S, save)
         with _nvtx("dfno.head"):
-            return self._head_forward(hcl)
+            out = self._head_forward(hcl)
+            return out.squeeze(2) if self.five_d else out
 
     def _backward(self, x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
         pl, C_ = self.plan, self._C
         x = x.contiguous()
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
+        if self.five_d and x.dim() == 5:
+            x, dy = x.unsqueeze(2), dy.unsqueeze(2)
         self._eval_mode = False
         hs, pres = self._saved["h"], self._saved["pre"]
         g = self.ws["g"]
@@ -903,23 +970,62 @@ class FusedDistributedFNO(nn.Module):
         return y
 
     # ------------------------------------------------------------------ canonical state <-> engine
-    def engine_state_to_global(self, to_all: bool = False):
-        """Canonical (partition independent) state on rank 0 / all ranks (CPU tensors)."""
+    def engine_meta(self) -> Dict[str, object]:
+        """What is needed to interpret this rank's flat ``theta`` outside the module (stored next to per-rank
+        checkpoints so that fused checkpoints can be assembled / re-sharded offline)."""
         pl = self.plan
-        mine = {}
-        for name, (off, shape) in pl.segments.items():
-            t = self._seg(name).detach().cpu()
+        return {"format": "fused-theta", "segments": dict(pl.segments), "C": pl.C, "kzl": pl.kzl, "kz_off": pl.kz_off,
+                "mt": pl.mt, "KX": pl.KX, "KY": pl.KY, "KZ": pl.KZ, "rank": self.rank, "world": self.world,
+                "num_blocks": self.num_blocks, "ndim": len(self.in_shape)}
+
+    @staticmethod
+    def theta_to_canonical(theta: torch.Tensor, meta: Dict[str, object], include_pointwise: bool = True):
+        """This rank's part of the canonical state from a flat ``theta`` (CPU tensor) and its :meth:`engine_meta`:
+        ``{name: tensor}`` for pointwise weights, ``{name: (kz_off, slab)}`` for spectral shards (global layout
+        ``[i, o, KX, KY, kzl, mt]``)."""
+        out = {}
+        C, kzl, mt, KX, KY = (int(meta[k]) for k in ("C", "kzl", "mt", "KX", "KY"))
+        for name, (off, shape) in meta["segments"].items():
+            t = theta[off:off + int(np.prod(shape))].view(shape).detach().cpu()
             if name.endswith(".spectral"):
                 # native [i, o, kzl, mt, KY, KX, 2] -> global slab [i, o, KX, KY, kzl, mt]
-                w = torch.view_as_complex(t.view(pl.C, pl.C, pl.kzl, pl.mt, pl.KY, pl.KX, 2).contiguous())
-                mine[name] = (pl.kz_off, w.permute(0, 1, 5, 4, 2, 3).contiguous())
-            elif self.rank == 0:
-                key, tt = name, t
+                w = torch.view_as_complex(t.reshape(C, C, kzl, mt, KY, KX, 2).contiguous())
+                out[name] = (int(meta["kz_off"]), w.permute(0, 1, 5, 4, 2, 3).contiguous())
+            elif include_pointwise:
+                tt = t
                 if name.endswith(".b"):
-                    b_shape = [1] * 6
+                    b_shape = [1] * int(meta.get("ndim", 6))
                     b_shape[-1 if name.startswith("linear1") else 1] = t.numel()
-                    tt = t.view(b_shape)
-                mine[key] = tt
+                    tt = t.reshape(b_shape)
+                out[name] = tt
+        return out
+
+    @staticmethod
+    def merge_canonical(parts, meta: Dict[str, object]) -> Dict[str, torch.Tensor]:
+        """Union of per-rank :meth:`theta_to_canonical` results."""
+        C, mt, KX, KY, KZ = (int(meta[k]) for k in ("C", "mt", "KX", "KY", "KZ"))
+        out: Dict[str, torch.Tensor] = {}
+        for part in parts:
+            for k, v in part.items():
+                if k.endswith(".spectral"):
+                    kz0, w = v
+                    if k not in out:
+                        out[k] = torch.zeros(C, C, KX, KY, KZ, mt, dtype=torch.complex64)
+                    out[k][:, :, :, :, kz0:kz0 + w.shape[4], :] = w
+                else:
+                    out[k] = v
+        nd = int(meta.get("ndim", 6))
+        for k in list(out):
+            if k.endswith(".spectral") and nd == 5:          # 2-D + time: drop the singleton kx axis
+                out[k] = out[k].squeeze(2)
+        for k in range(int(meta["num_blocks"])):          # key parity with the portable backend
+            out.setdefault(f"blocks.{k}.linear.b", torch.zeros(1, C, *([1] * (nd - 2))))
+        return out
+
+    def engine_state_to_global(self, to_all: bool = False):
+        """Canonical (partition independent) state on rank 0 / all ranks (CPU tensors)."""
+        meta = self.engine_meta()
+        mine = self.theta_to_canonical(self.theta.data, meta, include_pointwise=self.rank == 0)
         if self.world > 1:
             gathered = [None] * self.world
             dist.all_gather_object(gathered, mine, group=self.P_work.group)
@@ -927,28 +1033,25 @@ class FusedDistributedFNO(nn.Module):
             gathered = [mine]
         if not (to_all or self.rank == 0):
             return None
-        out = {}
-        for part in gathered:
-            for k, v in part.items():
-                if k.endswith(".spectral"):
-                    kz0, w = v
-                    if k not in out:
-                        out[k] = torch.zeros(pl.C, pl.C, pl.KX, pl.KY, pl.KZ, pl.mt, dtype=torch.complex64)
-                    out[k][:, :, :, :, kz0:kz0 + w.shape[4], :] = w
-                else:
-                    out[k] = v
-        for k in range(self.num_blocks):          # key parity with the portable backend
-            out.setdefault(f"blocks.{k}.linear.b", torch.zeros(1, pl.C, 1, 1, 1, 1))
-        return out
+        return self.merge_canonical(gathered, meta)
 
-    def engine_state_from_global(self, state) -> None:
+    def engine_state_from_global(self, state, strict: bool = True) -> None:
+        """Load a canonical state.  ``strict``: every engine segment must be present; otherwise missing segments
+        keep their values -- but a state that matches NO segment is always an error (it used to load nothing,
+        silently)."""
         pl = self.plan
+        missing = [n for n in pl.segments if n not in state]
+        if missing and (strict or len(missing) == len(pl.segments)):
+            raise KeyError(f"canonical state lacks {len(missing)} of {len(pl.segments)} engine segments, e.g. "
+                           f"{missing[:3]} (keys present: {sorted(state)[:4]}...)")
         with torch.no_grad():
             for name, (off, shape) in pl.segments.items():
                 if name not in state:
                     continue
                 src = state[name]
                 if name.endswith(".spectral"):
+                    if self.five_d and src.dim() == 5:
+                        src = src.unsqueeze(2)
                     w = src[:, :, :, :, pl.kz_off:pl.kz_off + pl.kzl, :].to(torch.complex64)
                     w = torch.view_as_real(w.permute(0, 1, 4, 5, 3, 2).contiguous())   # [i,o,kzl,mt,KY,KX,2]
                     self._seg(name).copy_(w.reshape(shape).to(self.device))

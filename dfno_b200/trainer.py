@@ -102,6 +102,10 @@ class Trainer:
             try:
                 self._gx, self._gy = torch.empty_like(xd), torch.empty_like(yd)
                 self._gx.copy_(xd); self._gy.copy_(yd)
+                # the warm-up steps and the capture pass must not train: snapshot parameters / optimizer state and
+                # put them back afterwards (in place -- the captured graph holds these very tensors), so the first
+                # batch gets exactly one update and host / device step counters agree
+                snap = self._snapshot_training_state()
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):                 # warm-up off the capturing stream
@@ -115,6 +119,7 @@ class Trainer:
                 with torch.cuda.graph(graph):
                     self._gloss = self._eager(self._gx, self._gy).detach()
                 self.graph_kernel_launches = getattr(counter, "count", 0) - c0
+                self._restore_training_state(snap)
                 self._graph = graph
                 self._graph_steps_py = getattr(self.optimizer, "step_count", None)
             except Exception as e:                            # noqa: BLE001 - capture is an optimisation
@@ -133,6 +138,42 @@ class Trainer:
         if hasattr(counter, "count"):
             counter.count += self.graph_kernel_launches
         return self._gloss
+
+    # -------------------------------------------------------------------- state snapshot around graph capture
+    @torch.no_grad()
+    def _snapshot_training_state(self):
+        opt = self.optimizer
+        snap = {"params": [(p, p.detach().clone()) for p in self.model.parameters()], "tensors": [], "attrs": {}}
+        if hasattr(opt, "m") and hasattr(opt, "v"):                      # FusedAdam: flat moment buffers + counters
+            for name in ("m", "v", "step_dev"):
+                t = getattr(opt, name, None)
+                if torch.is_tensor(t):
+                    snap["tensors"].append((t, t.clone()))
+            snap["attrs"]["step_count"] = getattr(opt, "step_count", 0)
+        elif hasattr(opt, "state"):                                      # torch.optim.*: per-parameter state dicts
+            snap["had_state"] = {id(p) for p in opt.state}
+            for st in opt.state.values():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        snap["tensors"].append((v, v.clone()))
+        return snap
+
+    @torch.no_grad()
+    def _restore_training_state(self, snap) -> None:
+        for p, v in snap["params"]:
+            p.data.copy_(v)
+        for t, v in snap["tensors"]:
+            t.copy_(v)
+        opt = self.optimizer
+        for k, v in snap["attrs"].items():
+            setattr(opt, k, v)
+        if "had_state" in snap:               # state created during the warm-up: zero it (lazy init happened there)
+            for p, st in opt.state.items():
+                if id(p) not in snap["had_state"]:
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.zero_()
+        torch.cuda.synchronize(self.device)
 
     @torch.no_grad()
     def evaluate(self, x_host: torch.Tensor, y_host: torch.Tensor) -> float:

@@ -101,7 +101,7 @@ def load_global_state(model, state: Optional[Dict[str, torch.Tensor]], src_is_ro
         dist.broadcast_object_list(box, src=P_x.world_ranks[0], group=P_x.group)
         state = box[0]
     if _is_fused(net):
-        net.engine_state_from_global(state)
+        net.engine_state_from_global(state, strict=strict)
         return
     own = net.state_dict()
     new: Dict[str, torch.Tensor] = {}
@@ -127,6 +127,10 @@ def load_global_state(model, state: Optional[Dict[str, torch.Tensor]], src_is_ro
             raise KeyError(name)
         else:
             new[name] = t
+    if not strict and state and not any(
+            (re.match(r"blocks\.(\d+)\.weights\.(\d+)$", n) and f"blocks.{n.split('.')[1]}.spectral" in state) or n in state
+            for n in own):
+        raise KeyError(f"canonical state matches no parameter of the model (keys: {sorted(state)[:4]}...)")
     net.load_state_dict(new, strict=strict)
 
 
@@ -144,12 +148,18 @@ def save_checkpoint(model, out_dir: str, epoch: Optional[int] = None, optimizer=
     """Write this rank's files.  Returns the model file path."""
     net = _unwrap(model)
     P = P or net.P_x
-    rank = max(P.rank, 0)
+    if not P.active:                # a world rank outside P_x owns nothing: it must not clobber rank 0's files
+        return ""
+    rank = P.rank
     os.makedirs(out_dir, exist_ok=True)
     path = checkpoint_path(out_dir, rank, epoch)
     torch.save(net.state_dict(), path)
+    extra = dict(extra or {})
+    extra.setdefault("plan", "fused" if _is_fused(net) else getattr(net, "plan_kind", extra.get("plan", "reference")))
     train_state = {
         "epoch": epoch,
+        "format": "fused-theta" if _is_fused(net) else "portable",
+        "engine": net.engine_meta() if _is_fused(net) else None,
         # the grid the *layers* are sharded over (differs from P_x when time/channel workers were folded)
         "partition": tuple(int(s) for s in getattr(net, "P_work", P).shape),
         "world_ranks": P.world_ranks,
@@ -157,7 +167,7 @@ def save_checkpoint(model, out_dir: str, epoch: Optional[int] = None, optimizer=
         "rng_cpu": torch.get_rng_state(),
         "rng_cuda": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
         "rng_numpy": np.random.get_state(),
-        "extra": extra or {},
+        "extra": extra,
     }
     torch.save(train_state, checkpoint_path(out_dir, rank, epoch, kind="train"))
     return path
@@ -169,7 +179,9 @@ def load_checkpoint(model, out_dir: str, epoch: Optional[int] = None, optimizer=
     plus ``epoch``."""
     net = _unwrap(model)
     P = P or net.P_x
-    rank = max(P.rank, 0)
+    if not P.active:
+        return {}
+    rank = P.rank
     sd = torch.load(checkpoint_path(out_dir, rank, epoch), map_location=map_location, weights_only=False)
     net.load_state_dict(sd)
     tpath = checkpoint_path(out_dir, rank, epoch, kind="train")
@@ -209,6 +221,20 @@ def assemble_global_from_files(src_dir: str, grid_x, block_in_shape, modes, epoc
     number of ranks, or offline)."""
     from ..parallel.planner import corner_boxes, make_pencil_plan, spectrum_shape
     from ..parallel.decomposition import index_of_rank
+    first = torch.load(checkpoint_path(src_dir, 0, epoch), map_location="cpu", weights_only=False)
+    if "theta" in first:            # files of the fused engine: one flat buffer per rank + its segment table
+        from ..models.fused import FusedDistributedFNO
+        parts, meta = [], None
+        for r in range(int(np.prod(grid_x))):
+            tpath = checkpoint_path(src_dir, r, epoch, kind="train")
+            if not os.path.exists(tpath):
+                raise FileNotFoundError(f"{tpath}: fused-engine checkpoints need the train_* file (segment table)")
+            meta = torch.load(tpath, map_location="cpu", weights_only=False).get("engine")
+            if not meta:
+                raise ValueError(f"{tpath} carries no engine segment table; it was written by an older version")
+            sd = first if r == 0 else torch.load(checkpoint_path(src_dir, r, epoch), map_location="cpu", weights_only=False)
+            parts.append(FusedDistributedFNO.theta_to_canonical(sd["theta"], meta, include_pointwise=r == 0))
+        return FusedDistributedFNO.merge_canonical(parts, meta)
     fft_shape = spectrum_shape(block_in_shape, modes)
     pp = make_pencil_plan(grid_x, kind=plan, spectrum=fft_shape)
     n_src = int(np.prod(grid_x))
@@ -244,5 +270,7 @@ def reshard_checkpoint(src_dir: str, dst_model, epoch: Optional[int] = None, src
     meta = torch.load(tpath, weights_only=False) if os.path.exists(tpath) else {}
     grid = tuple(src_grid) if src_grid is not None else tuple(meta["partition"])
     plan = src_plan or meta.get("extra", {}).get("plan", "reference")
+    if plan == "fused":
+        plan = "reference"          # irrelevant for theta files (assemble_global_from_files reads the segment table)
     state = assemble_global_from_files(src_dir, grid, net.block_in_shape, net.modes, epoch, plan)
     load_global_state(dst_model, state, strict=False)

@@ -142,6 +142,42 @@ def test_stage_plan_reproduces_spectral_convolution(P, staged, max_n):
     assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs)), (lhs, rhs)
 
 
+@pytest.mark.parametrize("P,staged", [(1, False), (2, False), (4, True), (2, "r3")])
+def test_stage_plan_2d_plus_time_runs_as_singleton_x(P, staged):
+    """A 5-D problem [B, C, X', Y', T] is the 6-D engine plan with X = 1: the x stages vanish and G2 / iG2 talk to
+    the mix directly.  Oracle: the portable 5-D block (reference semantics, dfno.py:82-97 with n = 3)."""
+    import dfno_b200 as d
+    B, C, Xp, Yp, T = 2, 3, 8, 8, 6
+    modes3 = (2, 2, 3)
+    torch.manual_seed(1)
+    _, P1, _ = d.create_standard_partitions((1, 1, 1, 1, 1))
+    blk = d.DistributedFNOBlock(P1, [B, C, Xp, Yp, T], modes3, dtype=torch.float64)
+    Wg = torch.zeros(C, C, *blk.fft_shape[2:], dtype=torch.complex128)
+    for w, sl in zip(blk.weights, blk.slices):
+        Wg[sl] = w.detach()
+    x = torch.randn(B, C, Xp, Yp, T, dtype=torch.float64)
+    want = blk.spectral_forward(x).detach()
+    plans = []
+    for r in range(P):
+        pl = EnginePlan(B, 1, 1, C, T, 1, Xp, Yp, (0, *modes3), world=P, rank=r)
+        pl.finish(1)
+        plans.append(pl)
+    assert not plans[0].has_x and plans[0].KX == 1
+    assert [st["name"] for st in plans[0].chain() if st["name"] in ("G3", "iG3")] == []
+    ops = plans[0].operators()
+    h = x.unsqueeze(2).permute(0, 1, 2, 3, 5, 4).contiguous().numpy()          # [B, C, 1, Y=X', T, Z=Y']
+    src, weights = [], []
+    W6 = Wg.unsqueeze(2)                                                       # [C, C, KX=1, KY, KZ, mt]
+    for pl in plans:
+        src.append(h[:, :, :, pl.y_off:pl.y_off + pl.Yl].reshape(pl.BC, 1, pl.Yl, T, Yp))
+        wn = W6[:, :, :, :, pl.kz_off:pl.kz_off + pl.kzl, :].permute(0, 1, 4, 5, 3, 2).contiguous()
+        weights.append(wn.reshape(C, C, pl.Q).numpy())
+    outs = _run_chain(plans, ops, src, weights, staged=staged)
+    got = np.concatenate([o.reshape(B, C, 1, pl.Yl, T, Yp) for o, pl in zip(outs, plans)], axis=3)
+    got = torch.from_numpy(got).permute(0, 1, 2, 3, 5, 4).squeeze(2)
+    assert torch.allclose(got, want, atol=1e-10), float((got - want).abs().max())
+
+
 class _Grid:
     """Stand-in for a Partition: ``supports`` only looks at ``dim`` and ``shape``."""
 
@@ -157,12 +193,18 @@ def test_supports_covers_the_baseline_configs():
     assert supports(_Grid(1, 1, 2, 2, 2, 1), [1, 2, 256, 256, 256, 1], 16, 32, (12, 12, 12, 8))[0]
     # config 4: 64^3 x 32, width 24, 8 modes, 8-way time partition
     assert supports(_Grid(1, 1, 1, 1, 1, 8), [1, 1, 64, 64, 64, 1], 32, 24, (8, 8, 8, 8))[0]
-    # reference two-phase trainer: 60 x 60 x 64 x 30 on 4 ranks -> T % 4 != 0 -> portable backend
-    ok, why = supports(_Grid(1, 1, 1, 4, 1, 1), [1, 2, 60, 60, 64, 1], 30, 20, (12, 12, 12, 8))
-    assert not ok and "T%4" in why
+    # reference two-phase trainer: 60 x 60 x 64 x 30 on 4 ranks (T % 4 != 0: padded t pitch), and the in-module
+    # demo (dfno.py:359-366): 64^3 x 30 on (1,1,2,2,1,1)
+    assert supports(_Grid(1, 1, 1, 4, 1, 1), [1, 2, 60, 60, 64, 1], 30, 20, (12, 12, 12, 8))[0]
+    assert supports(_Grid(1, 1, 2, 2, 1, 1), [1, 1, 64, 64, 64, 1], 30, 20, (4, 4, 4, 8))[0]
+    ok, why = supports(_Grid(1, 1, 1, 4, 1, 1), [1, 2, 60, 60, 64, 1], 15, 20, (12, 12, 12, 8))
+    assert not ok and "T%2" in why
     assert not supports(_Grid(2, 1, 1, 4, 1, 1), [2, 1, 64, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]      # data parallel
     assert not supports(_Grid(1, 1, 1, 16, 1, 1), [1, 1, 64, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]     # > one NVSwitch box
-    assert not supports(_Grid(1, 1, 2, 2, 1), [1, 1, 64, 64, 1], 16, 20, (8, 8, 8))[0]               # 2-D + time
+    # 2-D + time (the reference's Navier-Stokes trainer, experiment_navier_stokes.py:22-35): singleton-x plan
+    assert supports(_Grid(1, 1, 2, 2, 1), [10, 1, 64, 64, 10], 40, 20, (4, 4, 4))[0]
+    assert supports(_Grid(1, 1, 1, 1, 1), [1, 1, 64, 64, 1], 16, 20, (8, 8, 8))[0]
+    assert not supports(_Grid(1, 1, 2, 2), [1, 1, 64, 64], 16, 20, (8, 8))[0]                        # 1-D + time
     assert not supports(_Grid(1, 1, 1, 1, 1, 1), [1, 1, 512, 64, 64, 1], 16, 20, (8, 8, 8, 8))[0]     # X > 256
 
 
@@ -216,17 +258,25 @@ def test_column_parts_address_the_same_elements():
 
 def test_cost_model_reproduces_measured_dram_traffic():
     """The per-kernel byte counts of the traffic model against the DRAM bytes ncu measured on a B200 for the
-    headline configuration (RESULTS.md, profiles/r1_ncu_*.json, launch list v3) -- within 8 % (the small stages see
-    some L2 hits)."""
+    headline configuration (RESULTS.md, profiles/r1_ncu_*.json, launch list v3 for the round-1 dataflow;
+    profiles/r2_launch_list_fused_1gpu.csv for the fused pointwise dataflow) -- within 8 % (the small stages see
+    some L2 hits; 12 % for spectral_out, whose U input is partly still in the 126 MB L2)."""
     pl = EnginePlan(1, 1, 1, 20, 20, 128, 128, 128, (12, 12, 12, 10), world=1, rank=0)
     pl.finish(4)
-    cm = pl.cost_model()
+    cm = pl.cost_model(legacy=True)
     got = {n: b / 1e9 for n, _, b, _ in cm["stages"]}
     measured_gb = {"G1a": 2.27, "G1b": 0.91, "G2": 0.35, "iG1b": 0.96, "bypass fwd": 6.66, "bypass bwd": 8.35,
                    "spectral_mix fwd": 0.46, "spectral_mix bwd": 0.87, "adam": 12.3, "head fwd": 2.2, "head bwd": 4.2}
     for k, v in measured_gb.items():
         assert abs(got[k] - v) / v < 0.08, (k, got[k], v)
     assert 20.0 < cm["hbm_floor_ms"] < 27.0 and cm["nvlink_bytes"] == 0
+    cm = pl.cost_model()                                   # round-2 dataflow: fused pointwise kernels
+    got = {n: b / 1e9 for n, _, b, _ in cm["stages"]}
+    measured_gb = {"G1a": 2.274, "G1b": 0.910, "G2": 0.354, "iG1b": 0.952, "spectral_out fwd": 5.624, "dpre_dw": 6.852,
+                   "head fwd": 1.835, "head bwd": 3.483 + 0.168, "adam": 12.33, "lift fwd": 1.622, "lift bwd": 1.686}
+    for k, v in measured_gb.items():
+        assert abs(got[k] - v) / v < (0.12 if k == "spectral_out fwd" else 0.08), (k, got[k], v)
+    assert 15.0 < cm["hbm_floor_ms"] < 21.0 and cm["nvlink_bytes"] == 0
     p8 = EnginePlan(1, 1, 1, 20, 20, 128, 128, 128, (12, 12, 12, 10), world=8, rank=0)
     p8.finish(4)
     c8 = p8.cost_model()

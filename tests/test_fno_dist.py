@@ -194,3 +194,18 @@ def _grads(net):
 def test_fold_onto_pencil_is_transparent(ws, grid):
     for err, gerr, perr in run_distributed(_fold, ws, grid):
         assert err < 1e-10 and gerr < 1e-10 and perr < 1e-10, (err, gerr, perr)
+
+
+def _replica_init(rank, ws):
+    import dfno_b200 as d
+    _, P_x, _ = d.create_standard_partitions((2, 1, 1, 1, 1))
+    torch.manual_seed(0)                                     # identical seeds: the root still consumes extra RNG
+    net = d.DistributedFNO(P_x, [2, 1, 8, 8, 1], 4, 3, (2, 2, 2), num_blocks=1, dtype=torch.float64, backend="torch")
+    return [float(w.detach().abs().sum()) for w in net.blocks[0].weights]
+
+
+def test_data_parallel_replicas_start_from_the_same_spectral_weights():
+    """on a batch-partitioned P_x every replica drew its own spectral shard and only the gradients
+    were synchronised; the replicas must hold equal weights right after construction (no load_global_state)."""
+    a, b = run_distributed(_replica_init, 2, timeout=300)
+    assert a == b and len(a) > 0, (a, b)

@@ -90,7 +90,8 @@ def test_dpre_dw_matches_reference(B, C, L, Z):
     assert rel(dW, dW_ref) < 2e-3, rel(dW, dW_ref)
 
 
-@pytest.mark.parametrize("B,X,Y,Z,T,C", [(2, 4, 3, 8, 4, 20), (1, 3, 5, 16, 6, 8), (1, 2, 2, 8, 30, 32)])
+@pytest.mark.parametrize("B,X,Y,Z,T,C", [(2, 4, 3, 8, 4, 20), (1, 3, 5, 16, 6, 8), (1, 2, 2, 8, 30, 32),
+                                         (1, 40, 32, 64, 10, 20)])     # 6400 tiles: ~43 per CTA, both epilogue groups
 def test_channel_major_head_forward_backward(B, X, Y, Z, T, C):
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(3)

@@ -16,7 +16,7 @@ def test_trainer_replays_the_step_from_a_cuda_graph():
     torch.manual_seed(0)
     net = d.DistributedFNO(P_x, in_shape, 8, 8, (4, 4, 4, 3), num_blocks=2, device=dev, dtype=torch.bfloat16)
     assert isinstance(net, d.FusedDistributedFNO)
-    opt = d.FusedAdam(net, lr=1e-3)
+    opt = d.FusedAdam(net, lr=1e-2)
     crit = d.DistributedRelativeLpLoss(P_x, engine=net)
     tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=True)
     x = torch.randn(*in_shape).pin_memory()
@@ -25,7 +25,7 @@ def test_trainer_replays_the_step_from_a_cuda_graph():
     losses = [tr.step(x, y, next_batch=(x, y)) for _ in range(6)]
     assert tr._graph is not None, "the step must be capturable (no host sync, no NCCL inside)"
     assert all(math.isfinite(l) and l > 0 for l in losses), losses
-    assert losses[-1] < 1.2 * losses[0], losses              # Adam on a fixed batch: no blow-up across replays
+    assert losses[-1] < 1.05 * losses[0], losses             # Adam on a fixed batch: no blow-up across replays
     assert not torch.equal(before, net.theta.detach())
     assert tr.h2d_bytes == (x.numel() + y.numel()) * 4 and tr.d2h_bytes == 4
     # evaluation does not touch the weights
