@@ -5,11 +5,6 @@
 
 #include "kernels.h"
 
-namespace dfno {   // csrc/tma_probe.cu (diagnostic only; declared here so kernels.h stays untouched)
-const char* tma_probe_4d(const void* src, const long long* dims, const long long* strides_elems, const int* box,
-                         const int* coords, void* out, cudaStream_t s);
-}
-
 namespace {
 
 int sm_count() {
@@ -172,23 +167,6 @@ void permute_u32(const at::Tensor& src, at::Tensor& dst, const std::vector<int64
                           cur_stream()), "permute_u32");
 }
 
-// raw shared-memory image of one 4-D TMA box (bf16, SWIZZLE_128B): dims / box / coords innermost first,
-// strides (elements) of dims 1..3
-at::Tensor tma_probe_4d(const at::Tensor& src, const std::vector<int64_t>& dims, const std::vector<int64_t>& strides,
-                        const std::vector<int64_t>& box, const std::vector<int64_t>& coords) {
-  TORCH_CHECK(src.is_cuda() && src.scalar_type() == at::kBFloat16 && src.is_contiguous(), "src: contiguous CUDA bf16");
-  TORCH_CHECK(dims.size() == 4 && strides.size() == 3 && box.size() == 4 && coords.size() == 4, "4-D probe");
-  c10::cuda::CUDAGuard guard(src.device());
-  long long d[4], st[3];
-  int b[4], c[4];
-  int64_t vol = 1;
-  for (int i = 0; i < 4; ++i) { d[i] = dims[i]; b[i] = static_cast<int>(box[i]); c[i] = static_cast<int>(coords[i]); vol *= box[i]; }
-  for (int i = 0; i < 3; ++i) st[i] = strides[i];
-  at::Tensor out = at::zeros({vol * 2}, src.options().dtype(at::kByte));
-  check(dfno::tma_probe_4d(src.data_ptr(), d, st, b, c, out.data_ptr(), cur_stream()), "tma_probe_4d");
-  return out;
-}
-
 std::vector<at::Tensor> gelu_probe(const at::Tensor& x) {
   c10::cuda::CUDAGuard guard(x.device());
   at::Tensor y = at::empty_like(x), dy = at::empty_like(x);
@@ -293,5 +271,4 @@ void register_ops(pybind11::module& m) {
   m.def("gelu_probe", &gelu_probe);
   m.def("gelu_probe_h2", &gelu_probe_h2);
   m.def("permute_u32", &permute_u32);
-  m.def("tma_probe_4d", &tma_probe_4d);
 }

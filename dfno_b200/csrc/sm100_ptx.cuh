@@ -281,7 +281,6 @@ __device__ __forceinline__ GeluParts gelu_parts(float x) {
   return r;
 }
 struct GeluVG { float value; float grad; };                 // gelu(x) and d gelu / dx from one evaluation
-#ifndef DFNO_GELU_TANH3
 __device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const GeluParts g = gelu_parts(x);
@@ -291,44 +290,6 @@ __device__ __forceinline__ GeluVG gelu_value_grad(float x) {
   const GeluParts g = gelu_parts(x);
   return GeluVG{x * g.cdf, fmaf(x, g.pdf, g.cdf)};
 }
-#else
-// Candidate replacement (compile with -DDFNO_GELU_TANH3; not the default until measured on a B200):
-//   Phi(x) ~ 0.5 * (1 + tanh(x * (a + b x^2 + c x^4))),   x^2 clamped at 64,
-// coefficients fitted (minimax, x in [-8, 8]) to the *erf* form: |gelu err| <= 2.6e-5,
-// |gelu' err| <= 1.1e-4 before the MUFU.TANH error -- 8 instructions and one MUFU for the value
-// (A&S 7.1.26 above: 17 and two), 15 vs 20 for value + derivative.  The head kernels are bound by
-// exactly this instruction count (RESULTS.md).
-__device__ __forceinline__ float tanh_approx(float x) {
-  float r;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-struct GeluTanh { float half1pt; float t; float x2; };
-__device__ __forceinline__ GeluTanh gelu_tanh3_parts(float x) {
-  GeluTanh r;
-  r.x2 = fminf(x * x, 64.0f);
-  float g = fmaf(-3.51519787e-4f, r.x2, 3.70056658e-2f);
-  g = fmaf(g, r.x2, 7.97507861e-1f);
-  r.t = tanh_approx(x * g);
-  r.half1pt = fmaf(0.5f, r.t, 0.5f);
-  return r;
-}
-__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_tanh3_parts(x).half1pt; }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const GeluTanh r = gelu_tanh3_parts(x);
-  float gp = fmaf(5.0f * -3.51519787e-4f, r.x2, 3.0f * 3.70056658e-2f);
-  gp = fmaf(gp, r.x2, 7.97507861e-1f);
-  const float s = fmaf(-r.t, r.t, 1.0f);
-  return fmaf(0.5f * (x * s), gp, r.half1pt);
-}
-__device__ __forceinline__ GeluVG gelu_value_grad(float x) {
-  const GeluTanh r = gelu_tanh3_parts(x);
-  float gp = fmaf(5.0f * -3.51519787e-4f, r.x2, 3.0f * 3.70056658e-2f);
-  gp = fmaf(gp, r.x2, 7.97507861e-1f);
-  const float s = fmaf(-r.t, r.t, 1.0f);
-  return GeluVG{x * r.half1pt, fmaf(0.5f * (x * s), gp, r.half1pt)};
-}
-#endif
 // ------------------------------------------------------------------------------------------
 // packed fp16 GELU: two values per instruction (HFMA2 / one MUFU.TANH.F16x2 per PAIR)
 // ------------------------------------------------------------------------------------------

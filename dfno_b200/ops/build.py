@@ -22,14 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xptxas", "-v",
 ]
-# build-time experiments (each changes the source hash, so switching rebuilds):
-#   DFNO_GELU_TANH3=1  tanh-form erf-GELU approximant with one MUFU (csrc/sm100_ptx.cuh)
-_VARIANT = ""
-if os.environ.get("DFNO_GELU_TANH3", "0") != "0":
-    NVCC_FLAGS.append("-DDFNO_GELU_TANH3")
-    _VARIANT = "_tanh3"
-# every variant has its own in-tree directory, so both can be pre-built on a CPU box and travel together
-BUILD_DIR = os.path.normpath(os.path.join(_HERE, "..", "_build" + _VARIANT))
+BUILD_DIR = os.path.normpath(os.path.join(_HERE, "..", "_build"))
 
 _lock = threading.Lock()
 _mod = None

@@ -10,12 +10,12 @@
 #   smoke      __graft_entry__.smoke()                                                   ~20 s
 #   bench1     bench.py, 1 GPU, fused and baseline arms                                  ~2 min
 #   benchN     bench.py on $N GPUs, fused (+ DFNO_STAGED_SCATTER=0/1 A/B) and baseline   ~3 min
-#   refcompat  bench.py --impl reference-compat on 1 and $N GPUs                         ~3 min
+#   refarm     bench.py --impl reference (unmodified reference on baseline/compat) on 1 and $N GPUs   ~3 min
+#   mgtests    pytest tests/test_fused_multigpu.py tests/test_p2p_multigpu.py on all GPUs (log kept)   ~2 min
 #   exposed    benchmarks/exposed_a2a.py on $N GPUs (direct vs staged, same process)     ~40 s
 #   a2a        benchmarks/a2a_sweep.py on $N GPUs                                        ~1 min
 #   launches   ncu launch list of one training step (1 GPU)                              ~1 min
 #   ncu        ncu --set full of the top kernels (1 GPU; never a multi-rank command)     ~4 min
-#   gelu       DFNO_GELU_TANH3=1 variant (pre-built in-tree): probe error vs erf-GELU, 1-GPU bench            ~2 min
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -52,20 +52,17 @@ for stage in "$@"; do
                 trun "$N"; DFNO_STAGED_SCATTER=$s run 240 "bench_fused_${N}gpu_staged$s.json" $TR bench.py --gpus "$N" --steps 20 --warmup 5 --no-e2e
               done
               trun "$N"; run 300 "bench_baseline_${N}gpu.json" $TR bench.py --gpus "$N" --steps 6 --warmup 3 --impl baseline ;;
-    refcompat) run 400 bench_refcompat_1gpu.json python bench.py --gpus 1 --steps 3 --warmup 3 --impl reference-compat
-              trun "$N"; run 400 "bench_refcompat_${N}gpu.json" $TR bench.py --gpus "$N" --steps 4 --warmup 3 --impl reference-compat ;;
+    refarm)   run 400 bench_reference_1gpu.json python bench.py --gpus 1 --steps 4 --warmup 3 --impl reference
+              trun "$N"; run 400 "bench_reference_${N}gpu.json" $TR bench.py --gpus "$N" --steps 6 --warmup 3 --impl reference ;;
+    mgtests)  run 900 "multigpu_tests_${N}gpu.log" python -m pytest tests/test_fused_multigpu.py tests/test_p2p_multigpu.py -q -s -rxXs ;;
     exposed)  trun "$N"; run 120 "exposed_a2a_${N}gpu.log" $TR benchmarks/exposed_a2a.py ;;
     a2a)      trun "$N"; run 180 "a2a_sweep_${N}gpu.log" $TR benchmarks/a2a_sweep.py ;;
     launches) run 240 launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
                   --log-file "$OUT/launch_list.csv" python benchmarks/one_step.py ;;
-    ncu)      for k in dft_gemm head_bwd bypass_fwd_tc bypass_bwd_tc lift; do
+    ncu)      for k in dft_gemm head_bwd2 head_fwd spectral_out dpre_dw mix_ lift_bwd; do
                 run 240 "ncu_$k.log" ncu --set full --clock-control none --import-source on -k "regex:$k" -c 3 -f \
                     -o "$OUT/ncu_$k" python benchmarks/one_step.py
               done ;;
-    gelu)     # the variant is pre-built on the CPU side into dfno_b200/_build_tanh3 (DFNO_GELU_TANH3=1 python -c
-              # "from dfno_b200.ops import build; build.build()") and travels with the snapshot
-              DFNO_GELU_TANH3=1 run 200 gelu_probe.log python benchmarks/gelu_probe.py
-              DFNO_GELU_TANH3=1 run 300 bench_fused_1gpu_tanh3.json python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e ;;
     *) echo "unknown stage $stage"; exit 2 ;;
   esac
 done
