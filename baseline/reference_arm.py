@@ -63,7 +63,7 @@ def run(args, ClockSampler):
     N = args.gpus
     dev = torch.device("cuda", local) if on_gpu else torch.device("cpu")
     G, T = args.grid, args.nt
-    in_shape = [args.batch, args.in_channels, G, G, G, 1]
+    in_shape = [args.batch, args.in_channels, G, G, G, getattr(args, 'tin', 1)]
     grid = tuple(args.partition) if args.partition else (1, 1, 1, N, 1, 1)
     _, P_x, _ = ref.create_standard_partitions(grid)          # joins the torchrun job (mpirun's role)
     world = dist.get_world_size() if dist.is_initialized() else 1

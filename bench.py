@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--in-channels", type=int, default=1)
+    ap.add_argument("--tin", type=int, default=1, help="input time steps (BASELINE config 4 partitions the time axis: use 8)")
     ap.add_argument("--partition", type=int, nargs=6, default=None,
                     help="P_x (default 1 1 1 GPUS 1 1); other grids run the other BASELINE configs, e.g. "
                          "--grid 256 --nt 16 --width 32 --modes 12 12 12 8 --in-channels 2 --partition 1 1 2 2 2 1")
@@ -151,7 +152,7 @@ def main():
     cdtype = torch.bfloat16 if on_gpu else torch.float32      # compute dtype of the fused / baseline arms
 
     G, T = args.grid, args.nt
-    in_shape = [args.batch, args.in_channels, G, G, G, 1]
+    in_shape = [args.batch, args.in_channels, G, G, G, args.tin]
     out_shape = [args.batch, 1, G, G, G, T]
     grid = tuple(args.partition) if args.partition else (1, 1, 1, N, 1, 1)
     if int(torch.tensor(grid).prod()) != N:
@@ -179,10 +180,12 @@ def main():
     # target: a smooth function of the input field plus noise, so the loss actually moves during the timed steps
     # (pure noise would pin the relative L2 loss at 1.0 and make the N-rank vs 1-rank loss check vacuous)
     tt = torch.arange(T, device=dev, dtype=torch.float32)
-    y_glob = 0.5 * x_glob[:, :1] * torch.cos(0.3 * tt) + 0.1 * torch.randn(*out_shape, device=dev, generator=gen)
+    y_glob = 0.5 * x_glob[:, :1, ..., :1] * torch.cos(0.3 * tt) + 0.1 * torch.randn(*out_shape, device=dev, generator=gen)
     xi, yi = d.compute_distribution_info(P_x, in_shape), d.compute_distribution_info(P_x, out_shape)
     x_host = x_glob[tuple(xi["slice"])].to(in_dtype).contiguous().cpu()
     y_host = y_glob[tuple(yi["slice"])].contiguous().cpu()
+    if args.partition:
+        args.no_parity = True            # general partitions are run for size (configs 3 / 4): a 1-rank replay would not fit
     keep_global = args.impl == "fused" and N > 1 and rank == 0 and not args.no_parity
     if not keep_global:
         del x_glob, y_glob

@@ -13,24 +13,36 @@
 namespace dfno {
 namespace {
 
+// Thread (q, g): mode q and the g-th quarter of the output (forward) / input (backward) channels, so a slab of
+// Q modes runs 4 Q threads: with the mode slab split over 8 GPUs a rank holds only ~17 k modes, and one thread
+// per mode (400 dependent weight loads each) left most of the machine idle.  threadIdx.x walks q: every weight
+// load of a warp is one contiguous 256-byte run.
+constexpr int kMixSplit = 4;
+constexpr int kMixQ = 64;                      // modes per block (blockDim = (64, 4))
+
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMixQ * kMixSplit)
 mix_fwd_kernel(const uint32_t* __restrict__ x, const float2* __restrict__ w, uint32_t* __restrict__ y, int B,
                long long Q) {
-  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < Q;
-       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+  constexpr int CG = C / kMixSplit;
+  const int o0 = threadIdx.y * CG;
+  for (long long q = blockIdx.x * static_cast<long long>(kMixQ) + threadIdx.x; q < Q;
+       q += static_cast<long long>(gridDim.x) * kMixQ) {
     for (int b = 0; b < B; ++b) {
       float2 xv[C];
 #pragma unroll
       for (int i = 0; i < C; ++i) xv[i] = unpack_bf16x2(x[(static_cast<long long>(b) * C + i) * Q + q]);
-#pragma unroll 2
-      for (int o = 0; o < C; ++o) {
+#pragma unroll
+      for (int oo = 0; oo < CG; ++oo) {
+        const int o = o0 + oo;
+        float2 r[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) r[i] = __ldg(&w[(static_cast<long long>(i) * C + o) * Q + q]);   // C loads in flight
         float ar = 0.f, ai = 0.f;
 #pragma unroll
         for (int i = 0; i < C; ++i) {
-          const float2 r = __ldg(&w[(static_cast<long long>(i) * C + o) * Q + q]);
-          ar = fmaf(xv[i].x, r.x, ar); ar = fmaf(-xv[i].y, r.y, ar);
-          ai = fmaf(xv[i].x, r.y, ai); ai = fmaf(xv[i].y, r.x, ai);
+          ar = fmaf(xv[i].x, r[i].x, ar); ar = fmaf(-xv[i].y, r[i].y, ar);
+          ai = fmaf(xv[i].x, r[i].y, ai); ai = fmaf(xv[i].y, r[i].x, ai);
         }
         y[(static_cast<long long>(b) * C + o) * Q + q] = pack_bf16x2(ar, ai);
       }
@@ -40,25 +52,30 @@ mix_fwd_kernel(const uint32_t* __restrict__ x, const float2* __restrict__ w, uin
 
 // one batch element per launch; dw (+)= conj(x) * dy ; dx = sum_o dy * conj(w)
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMixQ * kMixSplit)
 mix_bwd_kernel(const uint32_t* __restrict__ x, const float2* __restrict__ w, const uint32_t* __restrict__ dy,
                uint32_t* __restrict__ dx, float2* __restrict__ dw, int accumulate, long long Q) {
-  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < Q;
-       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+  constexpr int CG = C / kMixSplit;
+  const int i0 = threadIdx.y * CG;
+  for (long long q = blockIdx.x * static_cast<long long>(kMixQ) + threadIdx.x; q < Q;
+       q += static_cast<long long>(gridDim.x) * kMixQ) {
     float2 gv[C];
 #pragma unroll
     for (int o = 0; o < C; ++o) gv[o] = unpack_bf16x2(dy[static_cast<long long>(o) * Q + q]);
-#pragma unroll 2
-    for (int i = 0; i < C; ++i) {
+#pragma unroll
+    for (int ii = 0; ii < CG; ++ii) {
+      const int i = i0 + ii;
       const float2 xi = unpack_bf16x2(x[static_cast<long long>(i) * Q + q]);
+      float2 r[C];
+#pragma unroll
+      for (int o = 0; o < C; ++o) r[o] = __ldg(&w[(static_cast<long long>(i) * C + o) * Q + q]);
       float dr = 0.f, di = 0.f;
 #pragma unroll
       for (int o = 0; o < C; ++o) {
         const long long widx = (static_cast<long long>(i) * C + o) * Q + q;
-        const float2 r = __ldg(&w[widx]);
         // dy * conj(r)
-        dr = fmaf(gv[o].x, r.x, dr); dr = fmaf(gv[o].y, r.y, dr);
-        di = fmaf(gv[o].y, r.x, di); di = fmaf(-gv[o].x, r.y, di);
+        dr = fmaf(gv[o].x, r[o].x, dr); dr = fmaf(gv[o].y, r[o].y, dr);
+        di = fmaf(gv[o].y, r[o].x, di); di = fmaf(-gv[o].x, r[o].y, di);
         // conj(x) * dy
         float2 g;
         g.x = xi.x * gv[o].x + xi.y * gv[o].y;
@@ -87,8 +104,9 @@ mix_bwd_kernel(const uint32_t* __restrict__ x, const float2* __restrict__ w, con
 
 const char* spectral_mix_fwd(const void* x, const float* w, void* y, int B, int C, long long Q, cudaStream_t s) {
   if (Q <= 0) return nullptr;
-  const int grid = static_cast<int>((Q + 127) / 128);
-  DFNO_MIX_DISPATCH(C, (mix_fwd_kernel<kC><<<grid, 128, 0, s>>>(static_cast<const uint32_t*>(x),
+  const int grid = static_cast<int>((Q + kMixQ - 1) / kMixQ);
+  const dim3 block(kMixQ, kMixSplit);
+  DFNO_MIX_DISPATCH(C, (mix_fwd_kernel<kC><<<grid, block, 0, s>>>(static_cast<const uint32_t*>(x),
                                                                reinterpret_cast<const float2*>(w),
                                                                static_cast<uint32_t*>(y), B, Q)));
   cudaError_t e = cudaGetLastError();
@@ -98,13 +116,14 @@ const char* spectral_mix_fwd(const void* x, const float* w, void* y, int B, int 
 const char* spectral_mix_bwd(const void* x, const float* w, const void* dy, void* dx, float* dw, int accumulate,
                              int B, int C, long long Q, cudaStream_t s) {
   if (Q <= 0) return nullptr;
-  const int grid = static_cast<int>((Q + 127) / 128);
+  const int grid = static_cast<int>((Q + kMixQ - 1) / kMixQ);
+  const dim3 block(kMixQ, kMixSplit);
   for (int b = 0; b < B; ++b) {
     const uint32_t* xb = static_cast<const uint32_t*>(x) + static_cast<long long>(b) * C * Q;
     const uint32_t* gb = static_cast<const uint32_t*>(dy) + static_cast<long long>(b) * C * Q;
     uint32_t* dxb = static_cast<uint32_t*>(dx) + static_cast<long long>(b) * C * Q;
     const int acc = (accumulate || b > 0) ? 1 : 0;
-    DFNO_MIX_DISPATCH(C, (mix_bwd_kernel<kC><<<grid, 128, 0, s>>>(xb, reinterpret_cast<const float2*>(w), gb, dxb,
+    DFNO_MIX_DISPATCH(C, (mix_bwd_kernel<kC><<<grid, block, 0, s>>>(xb, reinterpret_cast<const float2*>(w), gb, dxb,
                                                                  reinterpret_cast<float2*>(dw), acc, Q)));
   }
   cudaError_t e = cudaGetLastError();
