@@ -142,37 +142,42 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // a_format lives in bits [7,10): 1 = BF16, 0 = F16
-    const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad) & ~(p.a_f16 ? (7u << 7) : 0u);
-    const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
+    // ONE thread runs the whole loop.  With the skinny stages (K = 20..48: 3 MMAs per 128-row tile, 60 k tiles)
+    // this warp's scalar work per tile -- not the tensor core, not HBM -- set the pace of the kernel
+    // (profiles/r2_ncu_G1b.json: TMA and epilogue both waiting on it), so the loop carries no integer division
+    // (stage / phase counters are incremental) and builds each operand descriptor with one 64-bit add.
     mbar_wait(bfull, 0);
-    uint32_t s = 0, ph = 0;
-    const int kbs = static_cast<int>(L.kbs);
-    int n = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      const int a = n % nacc;
-      mbar_wait(&tempty[a], ((n / nacc) & 1) ^ 1);
-      const uint32_t d_tmem = tmem_base + a * p.n_pad;
-      const uint32_t b_base = smem_u32(smem_b);
-      for (int kb0 = 0; kb0 < kblocks; kb0 += kbs) {
-        mbar_wait(&full[s], ph);
-        tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = smem_u32(smem_a + s * L.a_tile_bytes);
+    if (lane == 0) {
+      // a_format lives in bits [7,10): 1 = BF16, 0 = F16
+      const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad) & ~(p.a_f16 ? (7u << 7) : 0u);
+      const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
+      const int kbs = static_cast<int>(L.kbs);
+      const uint64_t bdesc0 = umma_smem_desc_k128(smem_u32(smem_b));
+      const uint64_t adesc0 = umma_smem_desc_k128(smem_u32(smem_a));
+      const uint32_t a_stage16 = L.a_tile_bytes >> 4;              // descriptor address units are 16 bytes
+      const uint32_t b_kb16 = static_cast<uint32_t>(p.n_pad) * 128 >> 4;
+      uint32_t s = 0, ph = 0, a = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[a], aph ^ 1);
+        const uint32_t d_tmem = tmem_base + a * p.n_pad;
+        for (int kb0 = 0; kb0 < kblocks; kb0 += kbs) {
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          const uint64_t adesc_s = adesc0 + s * a_stage16;
           const int ks_end = min(ksteps, (kb0 + kbs) * 4);
           for (int ks = kb0 * 4; ks < ks_end; ++ks) {
-            const int kb = ks >> 2, kk = ks & 3;
-            const uint64_t adesc = umma_smem_desc_k128(a_base + (kb - kb0) * (kTileM * 128) + kk * 32);
-            const uint64_t bdesc = umma_smem_desc_k128(b_base + kb * (p.n_pad * 128) + kk * 32);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+            const uint32_t kb = ks >> 2, kk = ks & 3;
+            umma_bf16_ss(d_tmem, adesc_s + ((kb - kb0) * (kTileM * 128 >> 4) + kk * 2),
+                         bdesc0 + (kb * b_kb16 + kk * 2), idesc, ks > 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);             // smem stage may be refilled once the MMAs retire
           if (kb0 + kbs >= kblocks) umma_commit(&tfull[a]);   // accumulator ready for the epilogue
+          if (++s == L.stages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == L.stages) { s = 0; ph ^= 1; }
+        if (++a == static_cast<uint32_t>(nacc)) { a = 0; aph ^= 1; }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue: TMEM -> registers -> global / peer memory ==========
     // E groups of 4 warps (one per TMEM lane quarter; hardware: warp w may only touch lanes
@@ -200,13 +205,15 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
     }
-    int n = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      if (n % E != g) continue;
-      const int a = n % nacc;
+    // this group drains the CTA's tiles g, g+E, ...: accumulator stage and phase advance without divisions
+    // (nacc is a multiple of E)
+    int a = g;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles;
+         tile += E * gridDim.x, a += E, aph ^= (a >= nacc ? 1u : 0u), a -= (a >= nacc ? nacc : 0)) {
       const long long row = static_cast<long long>(tile) * kTileM + r_in_tile;
       const bool row_ok = row < p.M;
-      mbar_wait(&tfull[a], (n / nacc) & 1);
+      mbar_wait(&tfull[a], aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * p.n_pad;
 
