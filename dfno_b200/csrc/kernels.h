@@ -72,6 +72,10 @@ const char* head_bwd(const void* hcl, long long npos, int C, int CP, const void*
                      const float* b3, const float* W4, const float* dout, int nrl, const int* R, const long long* SR,
                      void* gcl, float* gW3, float* gb3, float* gW4, float* gb4, int num_sms, cudaStream_t stream);
 
+// batched Stockham FFT along the contiguous axis with fused truncation / zero padding (fft_radix.cu)
+const char* fft_radix(const void* x, void* y, int bf16, int N, long long lines, int inverse, int in_real, int out_real,
+                      int one_sided, int m, int num_sms, cudaStream_t s);
+
 // ---- round-2 fused pointwise path (spectral_out_sm100.cu, dpre_dw_sm100.cu, head_sm100.cu) ----
 // Last stage of a Fourier layer + bypass conv (+ GELU): see spectral_out_sm100.cu.  U: bf16 [B*C, L, K1];
 // h / pre / out: bf16 [B*C, L, Z]; Bop: padded operator bf16 [n_pad, k_pad]; W: fp32 [C, C].

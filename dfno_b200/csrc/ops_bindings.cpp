@@ -197,6 +197,16 @@ void head_bwd(const at::Tensor& hcl, int64_t npos, int64_t C, int64_t CP, const 
                        fptr_mut(gb3), fptr_mut(gW4), fptr_mut(gb4), sm_count(), cur_stream()), "head_bwd");
 }
 
+void fft_radix(const at::Tensor& x, at::Tensor& y, int64_t N, int64_t lines, bool inverse, bool in_real, bool out_real,
+               bool one_sided, int64_t m) {
+  TORCH_CHECK(x.is_cuda() && y.is_cuda() && x.is_contiguous() && y.is_contiguous(), "contiguous CUDA tensors");
+  TORCH_CHECK(x.scalar_type() == y.scalar_type() && (x.scalar_type() == at::kFloat || x.scalar_type() == at::kBFloat16),
+              "fp32 or bf16 (same type in and out)");
+  c10::cuda::CUDAGuard guard(x.device());
+  check(dfno::fft_radix(x.data_ptr(), y.data_ptr(), x.scalar_type() == at::kBFloat16, static_cast<int>(N), lines,
+                        inverse, in_real, out_real, one_sided, static_cast<int>(m), sm_count(), cur_stream()), "fft_radix");
+}
+
 void spectral_out(const at::Tensor& U, const at::Tensor& h, const at::Tensor& Bop, const at::Tensor& W, bool transpose_w,
                   const c10::optional<at::Tensor>& pre, at::Tensor& out, int64_t B, int64_t C, int64_t L, int64_t Z,
                   int64_t K1, bool gelu, bool save_pre) {
@@ -248,6 +258,7 @@ void head_bwd2(const at::Tensor& h, const at::Tensor& W3aug, const at::Tensor& W
 }  // namespace
 
 void register_ops(pybind11::module& m) {
+  m.def("fft_radix", &fft_radix);
   m.def("spectral_out", &spectral_out);
   m.def("dpre_dw", &dpre_dw);
   m.def("head_fwd", &head_fwd);

@@ -95,8 +95,12 @@ class DistributedFNOBlock(nn.Module):
     """
 
     def __init__(self, P_x: Partition, in_shape: Sequence[int], modes: Sequence[int],
-                 device=torch.device("cpu"), dtype=torch.float32, plan: str = "reference"):
+                 device=torch.device("cpu"), dtype=torch.float32, plan: str = "reference",
+                 fft_impl: str = "torch"):
         super().__init__()
+        if fft_impl not in ("torch", "native"):
+            raise ValueError("fft_impl is 'torch' (cuFFT / MKL) or 'native' (csrc/fft_radix.cu on CUDA tensors)")
+        self.fft_impl = fft_impl
         self.P_x = P_x
         self.in_shape = [int(s) for s in in_shape]
         self.modes = [int(m) for m in modes]
@@ -183,6 +187,24 @@ class DistributedFNOBlock(nn.Module):
                           dim in self.restrict_suffixes)
 
     # ------------------------------------------------------------------ spectral path
+    # transform + truncate / pad + inverse transform along one axis: torch.fft (cuFFT / MKL) or, with
+    # ``fft_impl="native"`` on a GPU, the hand-written Stockham kernel with the truncation fused in (ops/fft.py)
+    def _fwd(self, x: torch.Tensor, d: int, real_input: bool) -> torch.Tensor:
+        m = self.modes[d - 2]
+        if self.fft_impl == "native" and x.numel() and x.is_cuda and x.dtype in (torch.float32, torch.complex64):
+            from ..ops.fft import fwd_transform
+            return fwd_transform(x, d, m, real_input)
+        return _keep_modes(_fft(x, d, 'rfft' if real_input else 'fft'), d, m, not real_input)
+
+    def _inv(self, y: torch.Tensor, d: int, n_full: int, real_output: bool) -> torch.Tensor:
+        m = self.modes[d - 2]
+        if self.fft_impl == "native" and y.numel() and y.is_cuda and y.dtype == torch.complex64:
+            from ..ops.fft import inv_transform
+            return inv_transform(y, d, n_full, real_output)
+        if real_output:
+            return _fft(_pad_modes(y, d, m, n_full // 2 + 1, False), d, 'irfft', n=n_full)
+        return _fft(_pad_modes(y, d, m, n_full, True), d, 'ifft')
+
     def spectral_forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x`` (P_x shard, real) -> spectral branch output (P_x shard, real)."""
         t = self.timer
@@ -192,31 +214,31 @@ class DistributedFNOBlock(nn.Module):
             x = self.R1(x)
         if self.P_m.active:
             full[rdim] = x.shape[rdim]
-            x = _keep_modes(_fft(x, rdim, 'rfft'), rdim, self.modes[rdim - 2], False)
+            x = self._fwd(x, rdim, True)
             for d in reversed(self.plan.dim_m[:-1]):
                 full[d] = x.shape[d]
-                x = _keep_modes(_fft(x, d, 'fft'), d, self.modes[d - 2], True)
+                x = self._fwd(x, d, False)
         with t:
             x = self.R2(x)
         if self.P_y.active:
             for d in reversed(self.plan.dim_y):
                 full[d] = x.shape[d]
-                x = _keep_modes(_fft(x, d, 'fft'), d, self.modes[d - 2], True)
+                x = self._fwd(x, d, False)
             # the corners tile the whole local slab, so every entry is written exactly once;
             # a rank that owns no modes keeps a (differentiable) empty tensor
             y = torch.empty_like(x) if len(self.weights) else x * 0
             for w, sl in zip(self.weights, self.slices):
                 y[sl] = torch.einsum(self.eqn, x[sl], replica_grad_sync(w, self.replica_group))
             for d in self.plan.dim_y:
-                y = _fft(_pad_modes(y, d, self.modes[d - 2], full[d], True), d, 'ifft')
+                y = self._inv(y, d, full[d], False)
         else:
             y = x
         with t:
             y = self.R3(y)
         if self.P_m.active:
             for d in self.plan.dim_m[:-1]:
-                y = _fft(_pad_modes(y, d, self.modes[d - 2], full[d], True), d, 'ifft')
-            y = _fft(_pad_modes(y, rdim, self.modes[rdim - 2], full[rdim] // 2 + 1, False), rdim, 'irfft', n=full[rdim])
+                y = self._inv(y, d, full[d], False)
+            y = self._inv(y, rdim, full[rdim], True)
         with t:
             y = self.R4(y)
         return y
@@ -250,7 +272,7 @@ class DistributedFNO(nn.Module):
     def __init__(self, P_x: Partition, in_shape: Sequence[int], out_timesteps: int, width: int,
                  modes: Sequence[int], num_blocks: int = 4, device=torch.device("cpu"),
                  dtype=torch.float32, plan: str = "reference", backend: str = "auto",
-                 init_seed: Optional[int] = None):
+                 init_seed: Optional[int] = None, fft_impl: str = "torch"):
         super().__init__()
         if init_seed is not None:       # reproducible draw (per rank; the fused engine's is partition independent)
             torch.manual_seed(int(init_seed) + 7919 * max(int(P_x.rank), 0))
@@ -292,7 +314,7 @@ class DistributedFNO(nn.Module):
         self.linear3 = BroadcastedLinear(P_x, self.width, 128, dim=1, **kw)
         self.linear4 = BroadcastedLinear(P_x, 128, 1, dim=1, **kw)
         self.blocks = nn.ModuleList(
-            DistributedFNOBlock(P_x, self.block_in_shape, self.modes, plan=plan, **kw)
+            DistributedFNOBlock(P_x, self.block_in_shape, self.modes, plan=plan, fft_impl=fft_impl, **kw)
             for _ in range(self.num_blocks))
         # constructed for state-dict parity, not part of the forward (reference :325-346)
         self.bn1 = DistributedBatchNorm(P_x, self.width, **kw)
