@@ -193,25 +193,20 @@ def main():
         x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
-    # ---- N-rank vs 1-rank, part 1: the forward of the freshly initialised model (same seed => same global model)
-    parity = None
+    # ---- N-rank vs 1-rank, part 1: the forward of the freshly initialised model, gathered on rank 0 (compared below)
+    parity, out_cat = None, None
     if args.impl == "fused" and N > 1 and not args.no_parity:
         with torch.no_grad():
             out_n = net(x_dev).float().contiguous()
         shards = [torch.empty_like(out_n) for _ in range(N)] if rank == 0 else None
         dist.gather(out_n, shards, dst=0)
         if rank == 0:
-            P_1 = d.Partition([0], [1] * 6)
-            net1, opt1 = build(P_1, "fused")
-            with torch.no_grad():
-                out_1 = net1(x_glob).float()
-            out_cat = torch.empty_like(out_1)
+            out_cat = torch.empty(*out_shape, device=dev)
             for r, sh in enumerate(shards):                  # world rank r sits at grid index unravel(r, grid)
                 lo, hi = shard_bounds(out_shape, grid, [int(v) for v in np.unravel_index(r, grid)])
                 out_cat[assemble_slices(lo, hi)] = sh
-            parity = {"output_rel_err_vs_1rank_initial": float((out_cat - out_1).norm() / out_1.norm().clamp_min(1e-30))}
-            del out_cat, out_1, shards
-        del out_n
+            parity = {}
+        del out_n, shards
 
     use_graph = args.impl == "fused" and not args.no_graph
     tr = d.Trainer(net, crit, opt, device=dev, cuda_graph=use_graph)
@@ -277,9 +272,18 @@ def main():
                "cuda_graph": bool(tr._graph is not None),
                "how": "Trainer.step(): pinned host batch -> async H2D (double buffered) -> fwd+loss+bwd+Adam -> loss D2H"}
 
-    # ---- N-rank vs 1-rank, part 2: rank 0 repeats the same number of optimisation steps on ONE GPU with the same
-    # model / data and compares the loss after the last step (not timed; the other ranks wait at the barrier)
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30 if on_gpu else None     # before the 1-rank replay below
+
+    # ---- N-rank vs 1-rank, part 2 (not timed; the other ranks wait at the barrier): rank 0 builds the SAME model
+    # (same seed) on ONE GPU, compares its initial output with the gathered N-rank one, repeats the same number of
+    # optimisation steps on the same global sample and compares the loss after the last step
     if parity is not None:
+        P_1 = d.Partition([0], [1] * 6)
+        net1, opt1 = build(P_1, "fused")
+        with torch.no_grad():
+            out_1 = net1(x_glob).float()
+        parity["output_rel_err_vs_1rank_initial"] = float((out_cat - out_1).norm() / out_1.norm().clamp_min(1e-30))
+        del out_cat, out_1
         crit1 = d.DistributedRelativeLpLoss(P_1)
         x1, y1 = x_glob.to(in_dtype), y_glob
         l1 = None
@@ -310,7 +314,7 @@ def main():
                        "step": "forward + DistributedRelativeLpLoss + backward + Adam"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "cuda_graph": bool(tr._graph is not None), "loss": loss_value, "loss_parity": parity,
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30 if on_gpu else None,
+            "peak_mem_gb": peak_mem,
         }
         print(json.dumps(out))
     if dist.is_initialized():

@@ -4,11 +4,12 @@ and a driver ``submit_<system>.sh`` -- the role of ``/root/reference/benchmarks/
 (Summit/Perlmutter tables at ``:119-161``), re-targeted at one-process-per-GPU ``torchrun``
 launches on NVSwitch boxes:
 
-* ``b200``  : one 8 x B200 box, y-pencil partitions ``(1,1,1,N,1,1)``, N = 1, 2, 4, 8
-* ``local`` : CPU/gloo development runs, N <= 4
+* ``b200``        : one 8 x B200 box, 64^3 x 32 per GPU, the field grows in x, y and z (grids up to 2x2x2)
+* ``b200-pencil`` : the same box, 1 x N y-pencils at 128 x 16 x 128 x 20 per GPU
+* ``local``       : CPU/gloo development runs, N <= 4
 
-"spatial" grows the y extent (and its modes) with N at fixed per-GPU size; "temporal" keeps
-space fixed and grows ``nt`` and ``modes_t`` with N -- the reference's two scaling modes
+"spatial" grows the partitioned extents (and their modes) with the grid at fixed per-GPU size; "temporal"
+keeps space fixed and grows ``nt`` and ``modes_t`` with N -- the reference's two scaling modes
 (``gen_scripts.py:44-52``).  Zero-size shards are rejected at generation time (``:55-63``).
 """
 import os
@@ -16,19 +17,27 @@ from argparse import ArgumentParser
 from pathlib import Path
 
 ap = ArgumentParser()
-ap.add_argument("--system", default="b200", choices=["b200", "local"])
+ap.add_argument("--system", default="b200", choices=["b200", "b200-pencil", "local"])
 ap.add_argument("--max-workers", "-mw", type=int, default=-1)
 ap.add_argument("--clean-old", "-co", action="store_true")
 ap.add_argument("--out", type=Path, default=Path(os.path.dirname(os.path.abspath(__file__))))
 args = ap.parse_args()
 
 SYSTEMS = {
-    # per-GPU local shape (X, Y, Z, T), per-GPU modes, device, dtype
-    "b200": dict(shape=(128, 16, 128, 20), modes=(12, 2, 12, 10), device="cuda", dtype="bf16", counts=(1, 2, 4, 8)),
-    "local": dict(shape=(16, 8, 16, 8), modes=(4, 2, 4, 4), device="cpu", dtype="fp32", counts=(1, 2, 4)),
+    # per-GPU local shape (X, Y, Z, T), per-GPU modes, device, dtype, and the worker grids of the scaling series.
+    # "b200": one 8 x B200 NVSwitch box.  Like the reference's Perlmutter table (gen_scripts.py:141-153: 64^3 x 32 per
+    # GPU, 4 modes / axis / GPU) the volume grows in every spatial axis -- 1, 2, 4, 8 GPUs = (1,1,1), (1,2,1), (2,2,1),
+    # (2,2,2) -- so the 4- and 8-GPU points exercise the general-partition path (folded onto the engine's y-pencil);
+    # "b200-pencil" is the 1 x N y-pencil series (BASELINE config 2's layout) at 128 x 16 x 128 x 20 per GPU.
+    "b200": dict(shape=(64, 64, 64, 32), modes=(4, 4, 4, 4), device="cuda", dtype="bf16",
+                 grids={1: (1, 1, 1, 1, 1, 1), 2: (1, 1, 1, 2, 1, 1), 4: (1, 1, 2, 2, 1, 1), 8: (1, 1, 2, 2, 2, 1)}),
+    "b200-pencil": dict(shape=(128, 16, 128, 20), modes=(12, 2, 12, 10), device="cuda", dtype="bf16",
+                        grids={n: (1, 1, 1, n, 1, 1) for n in (1, 2, 4, 8)}),
+    "local": dict(shape=(16, 8, 16, 8), modes=(4, 2, 4, 4), device="cpu", dtype="fp32",
+                  grids={1: (1, 1, 1, 1, 1, 1), 2: (1, 1, 1, 2, 1, 1), 4: (1, 1, 2, 2, 1, 1)}),
 }
 cfg = SYSTEMS[args.system]
-counts = [n for n in cfg["counts"] if args.max_workers < 0 or n <= args.max_workers]
+counts = [n for n in cfg["grids"] if args.max_workers < 0 or n <= args.max_workers]
 
 
 def launcher(n):
@@ -37,14 +46,22 @@ def launcher(n):
 
 
 def point(n, mode):
+    """(global input shape, modes, nt, worker grid) of one scaling point.  "spatial": per-GPU block fixed, the global
+    field and its retained modes grow with the grid in every partitioned axis; "temporal": the global space of the
+    LARGEST grid stays fixed and nt / modes_t grow with the worker count (reference gen_scripts.py:44-52)."""
     X, Y, Z, T = cfg["shape"]
     mx, my, mz, mt = cfg["modes"]
-    part = (1, 1, 1, n, 1, 1)
+    part = cfg["grids"][n]
+    px, py, pz = part[2], part[3], part[4]
     if mode == "spatial":
-        shape, modes, nt = (1, 1, X, Y * n, Z, 1), (mx, my * n, mz, mt), T
+        shape, modes, nt = (1, 1, X * px, Y * py, Z * pz, 1), (mx * px, my * py, mz * pz, mt), T
     else:
-        shape, modes, nt = (1, 1, X, Y * max(cfg["counts"]), Z, 1), (mx, my * max(cfg["counts"]), mz, mt * n), T * n
-    if n > shape[3] or 2 * modes[1] > shape[3] or modes[3] > nt // 2 + 1 or (2 * modes[2]) % n:
+        big = cfg["grids"][max(cfg["grids"])]
+        shape = (1, 1, X * big[2], Y * big[3], Z * big[4], 1)
+        modes, nt = (mx * big[2], my * big[3], mz * big[4], mt * n), T * n
+    sp = shape[2:5]
+    if any(p > s for p, s in zip((px, py, pz), sp)) or any(2 * m > s for m, s in zip(modes[:3], sp)) \
+            or modes[3] > nt // 2 + 1:
         raise ValueError(f"invalid configuration {shape} / {modes} / {part}: a shard would be empty")
     return shape, modes, nt, part
 

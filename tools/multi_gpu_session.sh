@@ -28,6 +28,22 @@ for s in $STAGES; do
     cfg4)    run 240 "cfg4_fused_${N}gpu.json" $(tr) bench.py --gpus $N --steps 10 --warmup 3 --grid 64 --nt 32 --width 24 --modes 8 8 8 8 --tin 8 --partition $P4 ;;
     cfg4ref) run 300 "cfg4_reference_${N}gpu.json" $(tr) bench.py --gpus $N --steps 4 --warmup 3 --grid 64 --nt 32 --width 24 --modes 8 8 8 8 --tin 8 --partition $P4 --impl reference ;;
     cfg3)    run 300 "cfg3_fused_${N}gpu.json" $(tr) bench.py --gpus $N --steps 5 --warmup 3 --grid 256 --nt 16 --width 32 --modes 12 12 12 8 --in-channels 2 --partition $P3 ;;
+    weak)    # weak-scaling series (benchmarks/gen_scripts.py --system b200): every point with <= N ranks
+             (cd benchmarks && python gen_scripts.py --system b200 --clean-old > /dev/null
+              for n in 1 2 4 8; do [ $n -le $N ] || continue
+                for f in grad_weak_scaling_spatial_gpu grad_weak_scaling_temporal_gpu; do timeout 200 ./$f.sh $n > ../$OUT/weak_${f}_$n.log 2>&1; done
+              done
+              python - <<'PY' > ../gpurun_out/weak_scaling_summary.txt
+import glob, json, os
+rows = []
+for d in ("grad_weak_scaling_spatial_gpu", "grad_weak_scaling_temporal_gpu"):
+    for f in sorted(glob.glob(os.path.join(d, "*-0-*.json"))):
+        j = json.load(open(f)); n = int(f.rsplit("-", 1)[1].split(".")[0])
+        rows.append((d, n, os.path.basename(f), j.get("dt"), j.get("dt_grad"), j.get("dt_comm")))
+for r in sorted(rows):
+    print(f"{r[0]:34s} ranks {r[1]}  fwd {r[3]*1e3:8.3f} ms  bwd {r[4]*1e3:8.3f} ms  comm {r[5]*1e3:7.3f} ms   {r[2]}")
+PY
+             ); cat $OUT/weak_scaling_summary.txt ;;
     cfg3ref) run 400 "cfg3_reference_${N}gpu.json" $(tr) bench.py --gpus $N --steps 3 --warmup 3 --grid 256 --nt 16 --width 32 --modes 12 12 12 8 --in-channels 2 --partition $P3 --impl reference ;;
   esac
 done

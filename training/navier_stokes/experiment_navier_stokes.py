@@ -44,6 +44,8 @@ ap.add_argument("--batch-size", "-bs", type=int, default=10)
 ap.add_argument("--checkpoint-interval", "-ci", type=int, default=25)
 ap.add_argument("--generate-visualization", "-gv", action="store_true")
 ap.add_argument("--out-root", type=Path, default=Path("data"))
+ap.add_argument("--dtype", default="auto", choices=["auto", "bf16", "fp32"],
+                help="auto: bf16 on a GPU (the fused sm_100a engine serves 2-D + time problems), fp32 on the CPU")
 args = ap.parse_args()
 
 d.ensure_process_group()
@@ -92,13 +94,18 @@ with ctx:
     mu_y, std_y = local["mu_y"], local["std_y"]
     print(f"index = {P_x.index}, x_train.shape = {tuple(x_train.shape)}, y_train.shape = {tuple(y_train.shape)}")
 
-    n = x_train.shape[2] * int(P_x.shape[2]) if False else None
     gshape = d.infer_global_shape(P_x, [args.batch_size, *x_train.shape[1:]])
+    mdtype = {"auto": torch.bfloat16 if use_cuda else torch.float32, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
     net = d.DistributedFNO(P_x, gshape, T_out, args.width, args.modes, num_blocks=args.num_blocks, device=device,
-                           dtype=x_train.dtype)
+                           dtype=mdtype)
+    fused = isinstance(net, d.FusedDistributedFNO)
+    d.print0(f"backend = {'fused sm_100a engine' if fused else 'portable (torch.fft / torch.distributed)'}, dtype = {mdtype}")
     params = [p for p in net.parameters() if p.numel() > 0]
     criterion, mse = d.DistributedMSELoss(P_x).to(device), d.DistributedMSELoss(P_x).to(device)
-    optimizer = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-4)
+    optimizer = (d.FusedAdam(net, lr=1e-3, weight_decay=1e-4) if fused
+                 else torch.optim.Adam(params, lr=1e-3, weight_decay=1e-4))
+    if not fused:                                   # the fused engine takes fp32 / bf16 inputs as they are
+        x_train, x_test = x_train.to(mdtype), x_test.to(mdtype)
     steps, train_accs, test_accs = [], [], []
 
     for i in range(args.num_epochs):
@@ -143,4 +150,9 @@ with ctx:
                     if P_0.active:
                         np.savez(out_dir / f"gathered_{i + 1:04d}.npz", y_true=yt.cpu().numpy(), y_pred=yp.cpu().numpy(),
                                  steps=steps, train=train_accs, test=test_accs)
+                        # the reference's plots (experiment_navier_stokes.py:198-227): loss curves + truth / prediction GIF
+                        from dfno_b200.utils.viz import save_curves_png, save_field_gif
+                        save_curves_png(str(out_dir / f"curves_{i + 1:04d}.png"), {"train": train_accs, "test": test_accs})
+                        save_field_gif(str(out_dir / f"sample_{i + 1:04d}.gif"),
+                                       {"truth": yt[0, 0].float().cpu().numpy(), "prediction": yp[0, 0].float().cpu().numpy()})
 d.shutdown()

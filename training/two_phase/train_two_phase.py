@@ -58,6 +58,7 @@ with ctx:
 
     net = d.DistributedFNO(P_x, [nb, 2, *shape[:-1], 1], shape[-1], args.width, args.modes, device=device, dtype=dtype)
     fused = isinstance(net, d.FusedDistributedFNO)
+    d.print0(f"backend = {'fused sm_100a engine' if fused else 'portable (torch.fft / torch.distributed)'}, dtype = {dtype}")
     criterion = d.DistributedRelativeLpLoss(P_x).to(device)
     params = [p for p in net.parameters() if p.numel() > 0]
     optimizer = d.FusedAdam(net, lr=args.lr) if fused else (torch.optim.Adam(params, lr=args.lr) if params else None)
