@@ -65,7 +65,8 @@ def test_fused_engine_eligibility_rules():
     assert ok
     assert not supports(P6, [1, 1, 128, 128, 128, 1], 20, 21, (12, 12, 12, 10))[0]      # width
     assert not supports(P6, [1, 1, 128, 128, 100, 1], 20, 20, (12, 12, 12, 10))[0]      # Z % 8
-    assert not supports(d.Partition([0], [1] * 5), [1, 1, 64, 64, 1], 20, 20, (12, 12, 10))[0]
+    assert supports(d.Partition([0], [1] * 5), [1, 1, 64, 64, 1], 20, 20, (12, 12, 10))[0]      # 2-D + time (round 2)
+    assert not supports(d.Partition([0], [1] * 4), [1, 1, 64, 1], 20, 20, (12, 10))[0]             # 1-D + time: portable
     pl = EnginePlan(1, 1, 1, 20, 20, 128, 128, 128, (12, 12, 12, 10), world=8, rank=5)
     pl.finish(4)
     assert (pl.Yl, pl.kzl, pl.kz_off, pl.Q) == (16, 3, 15, 3 * 10 * 24 * 24)

@@ -32,7 +32,7 @@ def test_navier_stokes_trainer_runs_on_the_fused_engine(tmp_path):
     n = _nproc(4)
     grid = {1: ["1", "1", "1", "1", "1"], 2: ["1", "1", "2", "1", "1"], 4: ["1", "1", "2", "2", "1"]}[n]   # reference default: 2 x 2
     log = _run(["training/navier_stokes/experiment_navier_stokes.py", "--synthetic", "--grid", "64",
-                "--partition-shape", *grid, "--num-data", "24", "--in-timesteps", "10", "--out-timesteps", "40",
+                "--partition-shape", *grid, "--num-data", "40", "--train-split", "0.75", "--in-timesteps", "10", "--out-timesteps", "40",
                 "--num-epochs", "3", "--batch-size", "10", "--checkpoint-interval", "3", "--generate-visualization",
                 "--out-root", str(tmp_path / "ns")], n)
     assert "backend = fused sm_100a engine" in log, log[-2000:]
