@@ -35,7 +35,7 @@ def condense(vals):
                      if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio")
                      and "selected" not in k and f(k) == f(k)), reverse=True)[:4]
     pipes = {re.sub(r"^sm__inst_executed_pipe_(.*)\.avg.*", r"\1", k): round(f(k), 1) for k in hdr
-             if k.startswith("sm__inst_executed_pipe_") and k.endswith("pct_of_peak_sustained_active") and f(k) > 5}
+             if k.startswith("sm__inst_executed_pipe_") and k.endswith(".avg.pct_of_peak_sustained_active") and f(k) > 5}
     return {
         "kernel": re.sub(r"\(.*", "", m.get("Kernel Name", ""))[:80], "duration_ms": t * 1e3,
         "dram_read_GB": rd / 1e9, "dram_write_GB": wr / 1e9, "dram_TBps": (rd + wr) / t / 1e12,

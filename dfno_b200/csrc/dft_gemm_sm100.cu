@@ -94,7 +94,7 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   float* s_vec = reinterpret_cast<float*>(s_coloff + 128);              // [512] EPI_HEAD vectors
   uint8_t* s_colpeer = reinterpret_cast<uint8_t*>(s_vec + 512);         // [128] pair -> peer
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int kblocks = p.k_pad / kBlockK;
   const int num_tiles = (p.M + kTileM - 1) / kTileM;
@@ -142,20 +142,23 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // ONE thread runs the whole loop.  With the skinny stages (K = 20..48: 3 MMAs per 128-row tile, 60 k tiles)
-    // this warp's scalar work per tile -- not the tensor core, not HBM -- set the pace of the kernel
-    // (profiles/r2_ncu_G1b.json: TMA and epilogue both waiting on it), so the loop carries no integer division
-    // (stage / phase counters are incremental) and builds each operand descriptor with one 64-bit add.
+    // With the skinny stages (K = 20..48: 3 MMAs per 128-row tile, 60 k tiles) this warp's work per tile -- not
+    // the tensor core, not HBM -- set the pace of the kernel (profiles/r2_ncu_G1b.json: TMA and epilogue both
+    // waiting on it), so the loop carries no integer division (stage / phase counters are incremental).
+    // The WHOLE converged warp runs the loop on warp-uniform operands and one elected lane issues each instruction
+    // (umma_bf16_ss_k128_warp): with the loop inside `if (lane == 0)` the compiler kept the descriptors in vector
+    // registers and wrapped every UTCHMMA in an ELECT / R2UR waterfall loop, ~120 cycles per MMA on this warp.
     mbar_wait(bfull, 0);
-    if (lane == 0) {
+    {
       // a_format lives in bits [7,10): 1 = BF16, 0 = F16
       const uint32_t idesc = umma_idesc_bf16_f32(kTileM, p.n_pad) & ~(p.a_f16 ? (7u << 7) : 0u);
       const int ksteps = (p.K + 15) / 16;       // K=16 per instruction; zero tail needs no MMA
       const int kbs = static_cast<int>(L.kbs);
-      const uint64_t bdesc0 = umma_smem_desc_k128(smem_u32(smem_b));
-      const uint64_t adesc0 = umma_smem_desc_k128(smem_u32(smem_a));
+      const uint32_t bdesc0 = umma_k128_lo(smem_u32(smem_b));
+      const uint32_t adesc0 = umma_k128_lo(smem_u32(smem_a));
       const uint32_t a_stage16 = L.a_tile_bytes >> 4;              // descriptor address units are 16 bytes
       const uint32_t b_kb16 = static_cast<uint32_t>(p.n_pad) * 128 >> 4;
+      const uint32_t n_stages = L.stages;
       uint32_t s = 0, ph = 0, a = 0, aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[a], aph ^ 1);
@@ -163,16 +166,16 @@ dft_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb0 = 0; kb0 < kblocks; kb0 += kbs) {
           mbar_wait(&full[s], ph);
           tcgen05_fence_after();
-          const uint64_t adesc_s = adesc0 + s * a_stage16;
+          const uint32_t adesc_s = adesc0 + s * a_stage16;
           const int ks_end = min(ksteps, (kb0 + kbs) * 4);
           for (int ks = kb0 * 4; ks < ks_end; ++ks) {
             const uint32_t kb = ks >> 2, kk = ks & 3;
-            umma_bf16_ss(d_tmem, adesc_s + ((kb - kb0) * (kTileM * 128 >> 4) + kk * 2),
-                         bdesc0 + (kb * b_kb16 + kk * 2), idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss_k128_warp(d_tmem, adesc_s + ((kb - kb0) * (kTileM * 128 >> 4) + kk * 2),
+                                   bdesc0 + (kb * b_kb16 + kk * 2), idesc, ks > 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);             // smem stage may be refilled once the MMAs retire
-          if (kb0 + kbs >= kblocks) umma_commit(&tfull[a]);   // accumulator ready for the epilogue
-          if (++s == L.stages) { s = 0; ph ^= 1; }
+          umma_commit_warp(&empty[s]);        // smem stage may be refilled once the MMAs retire
+          if (kb0 + kbs >= kblocks) umma_commit_warp(&tfull[a]);   // accumulator ready for the epilogue
+          if (++s == n_stages) { s = 0; ph ^= 1; }
         }
         if (++a == static_cast<uint32_t>(nacc)) { a = 0; aph ^= 1; }
       }

@@ -46,7 +46,7 @@ dpre_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
   float* s_dw = reinterpret_cast<float*>(bars + 20);           // [C * C]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long num_tiles = p.tiles_per_b * p.B * p.nzb;
 
   for (uint32_t i = threadIdx.x; i < kStagesD * 3 * kBlkD / 16; i += blockDim.x)
@@ -85,25 +85,24 @@ dpre_dw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
+    // whole converged warp, warp-uniform operands, one elected lane issues (sm100_ptx.cuh: umma_bf16_ss_k128_warp)
     const uint32_t idesc = umma_idesc_bf16_f32(128, 128);
-    long long n = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      const uint32_t s = static_cast<uint32_t>(n % kStagesD);
+    const uint32_t ring_lo = umma_k128_lo(smem_u32(ring));
+    uint32_t s = 0, ph = 0, first = 1;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int zb = static_cast<int>(tile % p.nzb);
       const int ksteps = (min(64, p.Z - zb * 64) + 15) >> 4;       // columns beyond Z are zero-filled by TMA
-      mbar_wait(&pfull[s], (n / kStagesD) & 1);
+      mbar_wait(&pfull[s], ph);
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t dp = smem_u32(ring + s * 3 * kBlkD + kBlkD);
-        const uint32_t hh = dp + kBlkD;
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_bf16_ss(tmem_base, umma_smem_desc_k128(dp + kk * 32), umma_smem_desc_k128(hh + kk * 32), idesc,
-                       (n > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&mdone[s]);
-      }
-      __syncwarp();
+      const uint32_t dp = ring_lo + ((s * 3 * kBlkD + kBlkD) >> 4);
+      const uint32_t hh = dp + (kBlkD >> 4);
+      for (int kk = 0; kk < ksteps; ++kk)
+        umma_bf16_ss_k128_warp(tmem_base, dp + kk * 2, hh + kk * 2, idesc, (!first || kk > 0) ? 1u : 0u);
+      first = 0;
+      umma_commit_warp(&mdone[s]);
+      if (++s == kStagesD) { s = 0; ph ^= 1; }
     }
-    if (lane == 0) umma_commit(alldone);
+    umma_commit_warp(alldone);
     __syncwarp();
   } else {
     const int g = (warp - 2) >> 2;

@@ -98,7 +98,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
   uint32_t* s_w4 = reinterpret_cast<uint32_t*>(bars + 24);   // [64] fp16x2 pairs of W4 (16-byte aligned)
   float* s_b4 = reinterpret_cast<float*>(s_w4 + 64);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long num_tiles = p.tiles_per_b * p.B;
 
   for (uint32_t i = threadIdx.x; i < kStagesHF * stage_bytes / 16; i += blockDim.x)
@@ -145,21 +145,23 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__
     const uint32_t idesc = umma_idesc_bf16_f32(128, kHidH, /*A MN-major*/ 1, 0);
     const int ksteps = p.KR >> 4;
     mbar_wait(wfull, 0);
+    const uint32_t a16 = (smem_u32(s_a) & 0x3FFFFu) >> 4, w_lo = umma_k128_lo(smem_u32(s_w3));
+    const uint32_t a_lbo = ((half_bytes >> 4) & 0x3FFFu) << 16, mn_hi = umma_mn128_hi(1024);
     uint32_t s = 0, ph = 0;
-    long long n = 0;
+    uint32_t n = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      const int a = static_cast<int>(n & 3);
+      const uint32_t a = n & 3;
       mbar_wait(&tempty[a], ((n >> 2) & 1) ^ 1);
       mbar_wait(&full[s], ph);
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t abase = smem_u32(s_a + s * stage_bytes);
-        const uint32_t wbase = smem_u32(s_w3);
+      {
+        // whole converged warp, warp-uniform operands, one elected lane issues (sm100_ptx.cuh)
+        const uint32_t abase = a16 + ((s * stage_bytes) >> 4);
         for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16_ss(tmem_base + a * 128, umma_smem_desc_mn128(abase + ks * 2048, half_bytes, 1024),
-                       umma_smem_desc_k128(wbase + ks * 32), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&empty[s]);
-        umma_commit(&tfull[a]);
+          umma_f16_ss_lohi_warp(tmem_base + a * 128, (abase + ks * 128) | a_lbo, mn_hi, w_lo + ks * 2, kUmmaK128Hi, idesc,
+                                ks > 0 ? 1u : 0u);
+        umma_commit_warp(&empty[s]);
+        umma_commit_warp(&tfull[a]);
       }
       __syncwarp();
       if (++s == kStagesHF) { s = 0; ph ^= 1; }
@@ -249,7 +251,7 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
   float* s_gb4 = reinterpret_cast<float*>(bars + 28);
   uint32_t* s_w4h = reinterpret_cast<uint32_t*>(bars + 30);   // [64] fp16x2 pairs of W4 (16-byte aligned)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long num_tiles = p.tiles_per_b * p.B;
 
   for (uint32_t i = threadIdx.x; i < (p.stages + 2) * tile_bytes / 16; i += blockDim.x)
@@ -310,58 +312,64 @@ head_bwd2_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant_
     // Two epilogue groups work on alternate tiles (buffer index = tile parity).  MMA1 runs one tile AHEAD of the
     // reductions: MMA1(n+1) only needs the accumulator its own group drained early in tile n-1, so it is issued
     // before part2(n) blocks on that tile's P / ACT / hs -- no group ever waits for its next pre-activations.
-    auto mma1 = [&](long long k) {
-      const int buf = static_cast<int>(k & 1);
-      const uint32_t st = static_cast<uint32_t>(k % p.stages);
-      mbar_wait(&d1_empty[buf], ((k >> 1) & 1) ^ 1);
-      mbar_wait(&a_full[st], (k / p.stages) & 1);
+    // The whole converged warp runs these loops on warp-uniform operands and one elected lane issues each MMA
+    // (sm100_ptx.cuh: umma_f16_ss_lohi_warp).  Inside `if (lane == 0)` every one of the 26 MMAs of a tile was wrapped
+    // in an ELECT / R2UR waterfall loop (~120 cycles each): this warp, not the GELU math, set the pace of the kernel.
+    const uint32_t a16 = (smem_u32(s_a) & 0x3FFFFu) >> 4, w3_lo = umma_k128_lo(smem_u32(s_w3));
+    const uint32_t p16 = (smem_u32(s_p) & 0x3FFFFu) >> 4, act16 = (smem_u32(s_act) & 0x3FFFFu) >> 4;
+    const uint32_t hs16 = (smem_u32(s_hs) & 0x3FFFFu) >> 4, w3t_lo = umma_k128_lo(smem_u32(s_w3t));
+    const uint32_t a_lbo = ((half_bytes >> 4) & 0x3FFFu) << 16, p_lbo = ((16384u >> 4) & 0x3FFFu) << 16;
+    const uint32_t mn_hi = umma_mn128_hi(1024), klbo = 1u << 16;
+    const uint32_t tile16 = tile_bytes >> 4, half16 = half_bytes >> 4, n_st = static_cast<uint32_t>(p.stages);
+    uint32_t k1 = 0, st1 = 0, ph1 = 0;          // MMA1 tile counter, its ring stage and phase
+    uint32_t m2 = 0, st2 = 0;                   // part2 tile counter and ring stage
+    auto mma1 = [&]() {
+      const uint32_t buf = k1 & 1;
+      mbar_wait(&d1_empty[buf], ((k1 >> 1) & 1) ^ 1);
+      mbar_wait(&a_full[st1], ph1);
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t abase = smem_u32(s_a + st * tile_bytes);
-        const uint32_t wbase = smem_u32(s_w3);
-        for (int ks = 0; ks < k1steps; ++ks)
-          umma_bf16_ss(tmem_base + kHD1 + buf * 128, umma_smem_desc_mn128(abase + ks * 2048, half_bytes, 1024),
-                       umma_smem_desc_k128(wbase + ks * 32), idesc1, ks > 0 ? 1u : 0u);
-        umma_commit(&d1_full[buf]);
-      }
-      __syncwarp();
+      const uint32_t abase = a16 + st1 * tile16;
+      for (int ks = 0; ks < k1steps; ++ks)
+        umma_f16_ss_lohi_warp(tmem_base + kHD1 + buf * 128, (abase + ks * 128) | a_lbo, mn_hi, w3_lo + ks * 2, kUmmaK128Hi,
+                              idesc1, ks > 0 ? 1u : 0u);
+      umma_commit_warp(&d1_full[buf]);
+      ++k1;
+      if (++st1 == n_st) { st1 = 0; ph1 ^= 1; }
     };
-    auto part2 = [&](long long mth) {
-      const int pb = static_cast<int>(mth & 1);
-      const uint32_t st = static_cast<uint32_t>(mth % p.stages);
-      mbar_wait(&p_full[pb], (mth >> 1) & 1);
+    auto part2 = [&]() {
+      const uint32_t pb = m2 & 1;
+      mbar_wait(&p_full[pb], (m2 >> 1) & 1);
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t pbase = smem_u32(s_p + pb * 32768);
-        const uint32_t abase = smem_u32(s_act + pb * 32768);
-        const uint32_t hsbase = smem_u32(s_hs + pb * tile_bytes);
-        const uint32_t wtbase = smem_u32(s_w3t);
+      const uint32_t pbase = p16 + pb * (32768u >> 4);
+      const uint32_t abase = act16 + pb * (32768u >> 4);
+      const uint32_t hsbase = hs16 + pb * tile16;
+      const uint32_t acc0 = m2 > 0 ? 1u : 0u;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {            // K = hid
-          const int kb = ks >> 2, kk = ks & 3;
-          umma_bf16_ss(tmem_base + kHD2 + pb * 48, umma_smem_desc_k128(pbase + kb * 16384 + kk * 32),
-                       umma_smem_desc_k128(wtbase + kb * half_bytes + kk * 32), idesc2, ks > 0 ? 1u : 0u);
-        }
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {            // K = positions
-          const int kb = ks >> 2, kk = ks & 3;
-          const uint64_t bdesc = umma_smem_desc_k128(hsbase + kb * half_bytes + kk * 32);
-          umma_bf16_ss(tmem_base + kHD3, umma_smem_desc_mn128(pbase + ks * 2048, 16384, 1024), bdesc, idesc3,
-                       (mth > 0 || ks > 0) ? 1u : 0u);
-          umma_bf16_ss(tmem_base + kHD4, umma_smem_desc_mn128(abase + ks * 2048, 16384, 1024), bdesc, idesc3,
-                       (mth > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(&d2_full[pb]);
-        umma_commit(&a_empty[st]);
+      for (int ks = 0; ks < 8; ++ks) {            // K = hid
+        const uint32_t kb = ks >> 2, kk = ks & 3;
+        umma_f16_ss_lohi_warp(tmem_base + kHD2 + pb * 48, (pbase + kb * (16384u >> 4) + kk * 2) | klbo, kUmmaK128Hi,
+                              w3t_lo + kb * half16 + kk * 2, kUmmaK128Hi, idesc2, ks > 0 ? 1u : 0u);
       }
-      __syncwarp();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {            // K = positions
+        const uint32_t kb = ks >> 2, kk = ks & 3;
+        const uint32_t b_lo = (hsbase + kb * half16 + kk * 2) | klbo;
+        umma_f16_ss_lohi_warp(tmem_base + kHD3, (pbase + ks * 128) | p_lbo, mn_hi, b_lo, kUmmaK128Hi, idesc3,
+                              (ks > 0) ? 1u : acc0);
+        umma_f16_ss_lohi_warp(tmem_base + kHD4, (abase + ks * 128) | p_lbo, mn_hi, b_lo, kUmmaK128Hi, idesc3,
+                              (ks > 0) ? 1u : acc0);
+      }
+      umma_commit_warp(&d2_full[pb]);
+      umma_commit_warp(&a_empty[st2]);
+      ++m2;
+      if (++st2 == n_st) st2 = 0;
     };
-    if (nt > 0) mma1(0);
+    if (nt > 0) mma1();
     for (long long n = 0; n < nt; ++n) {
-      if (n + 1 < nt) mma1(n + 1);
-      part2(n);
+      if (n + 1 < nt) mma1();
+      part2();
     }
-    if (lane == 0) umma_commit(all_done);
+    umma_commit_warp(all_done);
     __syncwarp();
   } else {
     const int q = warp & 3;

@@ -76,6 +76,15 @@ const char* head_bwd(const void* hcl, long long npos, int C, int CP, const void*
 const char* fft_radix(const void* x, void* y, int bf16, int N, long long lines, int inverse, int in_real, int out_real,
                       int one_sided, int m, int num_sms, cudaStream_t s);
 
+// First two stages of a Fourier layer (truncated z-DFT then t-DFT) + the pencil transpose R2 in one kernel: see
+// spectral_in_sm100.cu.  dst_ptrs[j] (+ dst_off elements): rank j's S1 / S1s, viewed [B*C, kzl, mt, X, Yl*2] with
+// element strides dstr = {x, kt, kz, bc}.
+const char* spectral_in(const void* h, const void* op1, int n1_pad, int k1_pad, const void* op2, int n2_pad, int k2_pad,
+                        const long long* dst_ptrs, int P, long long dst_off, const long long* dstr, int BC, int X,
+                        int Yl, int T, int Z, int KZ, int mt, int num_sms, cudaStream_t stream);
+const char* spectral_in_check(int n1_pad, int k1_pad, int n2_pad, int k2_pad, int P, long long dst_off, const long long* dstr,
+                              int BC, int X, int Yl, int T, int Z, int KZ, int mt, int* cfg /* {Rp, Yc, E, stages} or null */);
+
 // ---- round-2 fused pointwise path (spectral_out_sm100.cu, dpre_dw_sm100.cu, head_sm100.cu) ----
 // Last stage of a Fourier layer + bypass conv (+ GELU): see spectral_out_sm100.cu.  U: bf16 [B*C, L, K1];
 // h / pre / out: bf16 [B*C, L, Z]; Bop: padded operator bf16 [n_pad, k_pad]; W: fp32 [C, C].

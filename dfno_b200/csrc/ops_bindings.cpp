@@ -218,6 +218,53 @@ void spectral_out(const at::Tensor& U, const at::Tensor& h, const at::Tensor& Bo
                            save_pre ? 1 : 0, sm_count(), cur_stream()), "spectral_out");
 }
 
+void spectral_in(const at::Tensor& h, const at::Tensor& op1, const at::Tensor& op2, const std::vector<int64_t>& dst_ptrs,
+                 int64_t dst_off, const std::vector<int64_t>& dstr, int64_t BC, int64_t X, int64_t Yl, int64_t T, int64_t Z,
+                 int64_t KZ, int64_t mt) {
+  TORCH_CHECK(op1.dim() == 2 && op1.is_contiguous() && op2.dim() == 2 && op2.is_contiguous(), "operators: contiguous [n_pad, k_pad]");
+  TORCH_CHECK(!dst_ptrs.empty() && dst_ptrs.size() <= 8 && dstr.size() == 4, "1..8 destinations, 4 strides");
+  TORCH_CHECK(h.numel() >= BC * X * Yl * T * Z, "activation smaller than its description");
+  c10::cuda::CUDAGuard guard(h.device());
+  long long ptrs[8], str[4];
+  for (size_t i = 0; i < dst_ptrs.size(); ++i) ptrs[i] = dst_ptrs[i];
+  for (size_t i = 0; i < 4; ++i) str[i] = dstr[i];
+  check(dfno::spectral_in(bptr(h), bptr(op1), static_cast<int>(op1.size(0)), static_cast<int>(op1.size(1)), bptr(op2),
+                          static_cast<int>(op2.size(0)), static_cast<int>(op2.size(1)), ptrs, static_cast<int>(dst_ptrs.size()),
+                          dst_off, str, static_cast<int>(BC), static_cast<int>(X), static_cast<int>(Yl), static_cast<int>(T),
+                          static_cast<int>(Z), static_cast<int>(KZ), static_cast<int>(mt), sm_count(), cur_stream()),
+        "spectral_in");
+}
+
+// "" when the fused front stage supports the shape, the reason otherwise (no launch, no device needed)
+std::string spectral_in_check(int64_t n1_pad, int64_t k1_pad, int64_t n2_pad, int64_t k2_pad, int64_t P, int64_t dst_off,
+                              const std::vector<int64_t>& dstr, int64_t BC, int64_t X, int64_t Yl, int64_t T, int64_t Z,
+                              int64_t KZ, int64_t mt) {
+  TORCH_CHECK(dstr.size() == 4, "4 strides");
+  long long str[4];
+  for (size_t i = 0; i < 4; ++i) str[i] = dstr[i];
+  const char* e = dfno::spectral_in_check(static_cast<int>(n1_pad), static_cast<int>(k1_pad), static_cast<int>(n2_pad),
+                                          static_cast<int>(k2_pad), static_cast<int>(P), dst_off, str, static_cast<int>(BC),
+                                          static_cast<int>(X), static_cast<int>(Yl), static_cast<int>(T), static_cast<int>(Z),
+                                          static_cast<int>(KZ), static_cast<int>(mt), nullptr);
+  return e ? std::string(e) : std::string();
+}
+
+// {positions per tile, positions per store chunk, epilogue groups, TMA ring stages} the kernel would use
+std::vector<int64_t> spectral_in_config(int64_t n1_pad, int64_t k1_pad, int64_t n2_pad, int64_t k2_pad, int64_t P,
+                                        int64_t dst_off, const std::vector<int64_t>& dstr, int64_t BC, int64_t X, int64_t Yl,
+                                        int64_t T, int64_t Z, int64_t KZ, int64_t mt) {
+  TORCH_CHECK(dstr.size() == 4, "4 strides");
+  long long str[4];
+  for (size_t i = 0; i < 4; ++i) str[i] = dstr[i];
+  int cfg[4] = {0, 0, 0, 0};
+  const char* e = dfno::spectral_in_check(static_cast<int>(n1_pad), static_cast<int>(k1_pad), static_cast<int>(n2_pad),
+                                          static_cast<int>(k2_pad), static_cast<int>(P), dst_off, str, static_cast<int>(BC),
+                                          static_cast<int>(X), static_cast<int>(Yl), static_cast<int>(T), static_cast<int>(Z),
+                                          static_cast<int>(KZ), static_cast<int>(mt), cfg);
+  TORCH_CHECK(!e, e);
+  return {cfg[0], cfg[1], cfg[2], cfg[3]};
+}
+
 void dpre_dw(const at::Tensor& g, at::Tensor& pre_dpre, const at::Tensor& h, at::Tensor& dW, int64_t B, int64_t C,
              int64_t L, int64_t Z) {
   c10::cuda::CUDAGuard guard(g.device());
@@ -259,6 +306,9 @@ void head_bwd2(const at::Tensor& h, const at::Tensor& W3aug, const at::Tensor& W
 
 void register_ops(pybind11::module& m) {
   m.def("fft_radix", &fft_radix);
+  m.def("spectral_in", &spectral_in);
+  m.def("spectral_in_check", &spectral_in_check);
+  m.def("spectral_in_config", &spectral_in_config);
   m.def("spectral_out", &spectral_out);
   m.def("dpre_dw", &dpre_dw);
   m.def("head_fwd", &head_fwd);

@@ -62,7 +62,7 @@ spectral_out_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
   uint64_t* bfull = bars + 16;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long num_tiles = p.tiles_per_b * p.B * p.nzt;
 
   // rows >= R*C of every operand block are never written by TMA: zero them once; build A2 = W (x) I_R
@@ -123,39 +123,41 @@ spectral_out_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     const int k1steps = (p.K1 + 15) >> 4;
     const int k2steps = (p.RC + 15) >> 4;
     mbar_wait(bfull, 0);
-    uint32_t s = 0, ph = 0;
-    long long n = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+    const uint32_t ring16 = (smem_u32(s_ring) & 0x3FFFFu) >> 4, b1_lo = umma_k128_lo(smem_u32(s_b1));   // address fields: 16-byte units
+    const uint32_t a2_lo = umma_k128_lo(smem_u32(s_a2));
+    const uint32_t mn_lbo = ((kBlk >> 4) & 0x3FFFu) << 16, mn_hi = umma_mn128_hi(1024);
+    uint32_t s = 0, ph = 0, a = 0, aph = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int zt = static_cast<int>(tile % p.nzt);
       const int ncols = min(128, p.Z - zt * 128);
       const uint32_t ntp = static_cast<uint32_t>((ncols + 15) & ~15);
-      const int a = static_cast<int>(n % kNAcc);
-      mbar_wait(&tempty[a], ((n / kNAcc) & 1) ^ 1);
+      mbar_wait(&tempty[a], aph ^ 1);
       mbar_wait(&full[s], ph);
       tcgen05_fence_after();
-      if (lane == 0) {
+      {
+        // whole converged warp, warp-uniform operands, one elected lane issues (sm100_ptx.cuh)
         const uint32_t d = tmem_base + a * kAccCols;
-        const uint32_t a1 = smem_u32(s_ring + s * p.stage_bytes);
-        const uint32_t b2 = a1 + p.k1blocks * kBlk;
-        const uint32_t b1 = smem_u32(s_b1) + zt * 128 * 128;
-        const uint32_t a2 = smem_u32(s_a2);
+        const uint32_t a1 = (ring16 + ((s * p.stage_bytes) >> 4)) | (1u << 16);          // K-major: LBO field = 1
+        const uint32_t b2 = (ring16 + ((s * p.stage_bytes + p.k1blocks * kBlk) >> 4)) | mn_lbo;   // MN-major: LBO = kBlk
+        const uint32_t b1 = b1_lo + ((zt * 128 * 128) >> 4);
         const uint32_t idesc1 = umma_idesc_bf16_f32(128, ntp);
         const uint32_t idesc2 = umma_idesc_bf16_f32(128, ntp, 0, /*B MN-major*/ 1);
         for (int ks = 0; ks < k1steps; ++ks) {
-          const int kb = ks >> 2, kk = ks & 3;
-          umma_bf16_ss(d, umma_smem_desc_k128(a1 + kb * kBlk + kk * 32),
-                       umma_smem_desc_k128(b1 + kb * (p.n_pad * 128) + kk * 32), idesc1, ks > 0 ? 1u : 0u);
+          const uint32_t kb = ks >> 2, kk = ks & 3;
+          umma_bf16_ss_k128_warp(d, a1 + ((kb * kBlk) >> 4) + kk * 2, b1 + ((kb * (p.n_pad * 128)) >> 4) + kk * 2, idesc1,
+                                 ks > 0 ? 1u : 0u);
         }
         for (int ks = 0; ks < k2steps; ++ks) {       // K = the tile's own rows (c, r): 16 rows per instruction
-          const int kb = ks >> 2, kk = ks & 3;
-          umma_bf16_ss(d, umma_smem_desc_k128(a2 + kb * kBlk + kk * 32),
-                       umma_smem_desc_mn128(b2 + ks * 2048, kBlk, 1024), idesc2, 1u);
+          const uint32_t kb = ks >> 2, kk = ks & 3;
+          umma_f16_ss_lohi_warp(d, a2_lo + ((kb * kBlk) >> 4) + kk * 2, kUmmaK128Hi, b2 + ((ks * 2048) >> 4), mn_hi,
+                                idesc2, 1u);
         }
-        umma_commit(&empty[s]);
-        umma_commit(&tfull[a]);
+        umma_commit_warp(&empty[s]);
+        umma_commit_warp(&tfull[a]);
       }
       __syncwarp();
       if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1; }
+      if (++a == kNAcc) { a = 0; aph ^= 1; }
     }
   } else {
     // ===================== epilogue: one thread per row (c, r) =====================

@@ -374,8 +374,9 @@ class EnginePlan:
         return out
 
     def cost_model(self, hbm_gbs: float = 6491.8, nvlink_gbs: float = 770.0,
-                   staged: Optional[bool] = None, legacy: bool = False) -> Dict[str, object]:
+                   staged: Optional[bool] = None, legacy: bool = False, front: bool = False) -> Dict[str, object]:
         """Bytes every kernel of one training step must move (per rank) and the resulting floors.
+        ``front``: G1a + G1b run as the single ``spectral_in`` kernel (Z1 stays on the SM).
 
         Pure bookkeeping of the dataflow in :class:`FusedDistributedFNO` -- each stage reads its input
         buffer and writes its output buffer once; nothing is assumed to stay in L2 (the working set of a
@@ -398,6 +399,8 @@ class EnginePlan:
         off = (P - 1) / P if P > 1 else 0.0
         chain = [("G1a", act + Z1, 0), ("G1b", Z1 + S1, S1 * off), ("G2", S1 + S2, 0), ("G3", S2 + S3, 0),
                  ("iG3", S3 + T2, 0), ("iG2", T2 + T1, T1 * off), ("iG1b", T1 + U, 0)]
+        if front and not legacy:
+            chain = [("spectral_in", act + S1, S1 * off)] + chain[2:]
         if not self.has_x:
             chain = [c for c in chain if c[0] not in ("G3", "iG3")]
         if legacy:
@@ -477,7 +480,7 @@ class _LaunchCounter:
 
     def __getattr__(self, name):
         fn = getattr(self._mod, name)
-        if name.startswith(("symm_", "tensor_from_ptr")):
+        if name.startswith(("symm_", "tensor_from_ptr")) or name.endswith("_check"):
             return fn
 
         def call(*a, **k):
@@ -613,6 +616,43 @@ class FusedDistributedFNO(nn.Module):
         # the channel-major activation directly (csrc/spectral_out_sm100.cu, dpre_dw_sm100.cu, head_sm100.cu).
         # DFNO_POINTWISE=legacy keeps round 1's separate bypass / channels-last head kernels for A/B runs.
         self.fused_pw = os.environ.get("DFNO_POINTWISE", "fused").lower() != "legacy" and 2 * pl.KZ <= 128
+        # the first two GEMMs of every chain (z-DFT, t-DFT) + the transpose R2 as ONE kernel that keeps Z1 on the SM
+        # (csrc/spectral_in_sm100.cu); DFNO_FRONT=legacy keeps the two dft_gemm launches for A/B runs.
+        self.front = None
+        if os.environ.get("DFNO_FRONT", "fused").lower() != "legacy":
+            self.front = self._front_plan()
+
+    def _front_plan(self) -> Optional[dict]:
+        """Destination view of ``spectral_in`` for this plan's S1 layout (direct or staged), or None when the kernel
+        does not support the shape (then G1a + G1b run as separate GEMMs)."""
+        pl = self.plan
+        P, r = max(self.world, 1), self.rank
+        staged_r2 = self.staged_scatter is True or self.staged_scatter == "r2"
+        X, Y, Yl, mt, kzl = pl.X, pl.Y, pl.Yl, pl.mt, pl.kzl
+        if staged_r2:        # S1s[bc, kz', kt, r_src, x, y_loc, ri] on the rank owning kz
+            dstr = [Yl * 2, P * X * Yl * 2, mt * P * X * Yl * 2, kzl * mt * P * X * Yl * 2]
+            off = r * X * Yl * 2
+        else:                # S1[bc, kz', kt, x, y, ri]
+            dstr = [Y * 2, X * Y * 2, mt * X * Y * 2, kzl * mt * X * Y * 2]
+            off = pl.y_off * 2
+        if "G1a" not in self.ops or "G1b" not in self.ops:
+            return None
+        o1, o2 = self.ops["G1a"], self.ops["G1b"]
+        why = self._C.spectral_in_check(o1.shape[0], o1.shape[1], o2.shape[0], o2.shape[1], P, off, dstr,
+                                        pl.BC, X, Yl, pl.T, pl.Z, pl.KZ, mt)
+        if why:
+            return None
+        return dict(dstr=dstr, off=off, dst="S1s" if staged_r2 else "S1")
+
+    def _front(self, src: torch.Tensor, adj: bool) -> None:
+        pl, fr = self.plan, self.front
+        if self.world > 1:
+            ptrs = self.sym_S1.peer_ptrs()
+        else:
+            ptrs = [self.ws[fr["dst"]].data_ptr()]
+        sfx = "_adj" if adj else ""
+        self._C.spectral_in(src, self.ops["G1a" + sfx], self.ops["G1b" + sfx], ptrs, fr["off"], fr["dstr"],
+                            pl.BC, pl.X, pl.Yl, pl.T, pl.Z, pl.KZ, pl.mt)
 
     # ------------------------------------------------------------------ parameters
     def _seg(self, name: str, base: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -737,7 +777,12 @@ class FusedDistributedFNO(nn.Module):
                 "U": ws["Z1U"], "dst": dst, "S1s": ws.get("S1s"), "T1s": ws.get("T1s")}
         R = self._seg(f"blocks.{block}.spectral")
         for st in self.chain_desc:
-            if st["name"].startswith("perm"):
+            if self.front is not None and st["name"] in ("G1a", "G1b"):
+                if st["name"] == "G1a":
+                    self._front(bufs["src"], adj)
+                elif st.get("barrier_after"):
+                    self.barrier()
+            elif st["name"].startswith("perm"):
                 self._C.permute_u32(bufs[st["src"]], bufs[st["dst"]], st["size"], st["sstr"], st["dstr"])
             elif st["name"] == "mix":
                 if adj:

@@ -277,8 +277,12 @@ def test_cost_model_reproduces_measured_dram_traffic():
     for k, v in measured_gb.items():
         assert abs(got[k] - v) / v < (0.12 if k == "spectral_out fwd" else 0.08), (k, got[k], v)
     assert 15.0 < cm["hbm_floor_ms"] < 21.0 and cm["nvlink_bytes"] == 0
+    cf = pl.cost_model(front=True)                         # + spectral_in: Z1 (0.63 GB written and re-read) is gone
+    assert abs((cm["hbm_bytes"] - cf["hbm_bytes"]) - 8 * 2 * pl.n_Z1 * 2) < 1e6
+    assert cf["hbm_floor_ms"] < cm["hbm_floor_ms"] - 1.4
     p8 = EnginePlan(1, 1, 1, 20, 20, 128, 128, 128, (12, 12, 12, 10), world=8, rank=0)
     p8.finish(4)
+    assert p8.cost_model(front=True)["nvlink_bytes"] == p8.cost_model()["nvlink_bytes"]
     c8 = p8.cost_model()
     per_chain = c8["nvlink_bytes"] / (2 * 4)
     assert abs(per_chain - 68.8e6) / 68.8e6 < 0.01        # bytes leaving a rank per spectral convolution
