@@ -85,6 +85,12 @@ const char* spectral_in(const void* h, const void* op1, int n1_pad, int k1_pad, 
 const char* spectral_in_check(int n1_pad, int k1_pad, int n2_pad, int k2_pad, int P, long long dst_off, const long long* dstr,
                               int BC, int X, int Yl, int T, int Z, int KZ, int mt, int* cfg /* {Rp, Yc, E, stages} or null */);
 
+// Elementwise part of the relative-L2 / MSE losses (loss.cu): per-sample sums of (y_hat - y)^2 and y^2 into
+// part[0..B) / part[B..2B), and grad = (y_hat - y) * scale[b].
+const char* sq_partials(const float* yh, const float* y, float* part, long long n_per_b, int B, int num_sms, cudaStream_t s);
+const char* scaled_diff(const float* yh, const float* y, const float* scale, float* grad, long long n_per_b, int B,
+                        int scale_per_b, int num_sms, cudaStream_t s);
+
 // ---- round-2 fused pointwise path (spectral_out_sm100.cu, dpre_dw_sm100.cu, head_sm100.cu) ----
 // Last stage of a Fourier layer + bypass conv (+ GELU): see spectral_out_sm100.cu.  U: bf16 [B*C, L, K1];
 // h / pre / out: bf16 [B*C, L, Z]; Bop: padded operator bf16 [n_pad, k_pad]; W: fp32 [C, C].

@@ -265,6 +265,25 @@ std::vector<int64_t> spectral_in_config(int64_t n1_pad, int64_t k1_pad, int64_t 
   return {cfg[0], cfg[1], cfg[2], cfg[3]};
 }
 
+void sq_partials(const at::Tensor& yh, const at::Tensor& y, at::Tensor& part, int64_t B) {
+  TORCH_CHECK(yh.is_cuda() && y.is_cuda() && yh.scalar_type() == at::kFloat && y.scalar_type() == at::kFloat &&
+              yh.is_contiguous() && y.is_contiguous() && yh.numel() == y.numel() && yh.numel() % B == 0, "fp32 contiguous fields");
+  TORCH_CHECK(part.scalar_type() == at::kFloat && part.numel() >= 2 * B && part.is_contiguous(), "part: 2B floats");
+  c10::cuda::CUDAGuard guard(yh.device());
+  check(dfno::sq_partials(fptr(yh), fptr(y), fptr_mut(part), yh.numel() / B, static_cast<int>(B), sm_count(), cur_stream()),
+        "sq_partials");
+}
+
+void scaled_diff(const at::Tensor& yh, const at::Tensor& y, const at::Tensor& scale, at::Tensor& grad, int64_t B) {
+  TORCH_CHECK(yh.is_cuda() && yh.scalar_type() == at::kFloat && y.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat &&
+              yh.is_contiguous() && y.is_contiguous() && grad.is_contiguous() && yh.numel() == y.numel() &&
+              grad.numel() == yh.numel() && yh.numel() % B == 0, "fp32 contiguous fields");
+  TORCH_CHECK(scale.scalar_type() == at::kFloat && (scale.numel() == 1 || scale.numel() == B), "scale: 1 or B floats");
+  c10::cuda::CUDAGuard guard(yh.device());
+  check(dfno::scaled_diff(fptr(yh), fptr(y), fptr(scale), fptr_mut(grad), yh.numel() / B, static_cast<int>(B),
+                          scale.numel() == B ? 1 : 0, sm_count(), cur_stream()), "scaled_diff");
+}
+
 void dpre_dw(const at::Tensor& g, at::Tensor& pre_dpre, const at::Tensor& h, at::Tensor& dW, int64_t B, int64_t C,
              int64_t L, int64_t Z) {
   c10::cuda::CUDAGuard guard(g.device());
@@ -306,6 +325,8 @@ void head_bwd2(const at::Tensor& h, const at::Tensor& W3aug, const at::Tensor& W
 
 void register_ops(pybind11::module& m) {
   m.def("fft_radix", &fft_radix);
+  m.def("sq_partials", &sq_partials);
+  m.def("scaled_diff", &scaled_diff);
   m.def("spectral_in", &spectral_in);
   m.def("spectral_in_check", &spectral_in_check);
   m.def("spectral_in_config", &spectral_in_config);

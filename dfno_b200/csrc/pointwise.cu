@@ -134,16 +134,21 @@ lift_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
   }
 }
 
-// dW1[T][Tin], db1[T], dW2[C][Cin], db2[C] accumulated with atomics into fp32 buffers.  Channel-indexed sums
-// stay in registers over the whole grid-stride loop; time-indexed sums are warp-reduced once per t.  The loss
-// gradient can be far below the fp16 range, so everything it multiplies is fp32; only the GELU' evaluations
-// are packed fp16.
+// dW1[T][Tin], db1[T], dW2[C][Cin], db2[C] accumulated with atomics into fp32 buffers.  Four adjacent lanes share
+// one item (8 consecutive z of one (b, x, y)) and split the C channels between them: a thread keeps C/4 channel
+// sums in registers over the whole grid-stride loop (with all C channels per thread the kernel needed 241
+// registers and ran at 12 % occupancy, 0.21 of copy bandwidth: profiles/r2_ncu_kernels.json), the input-gradient
+// partials of the four quarters meet in two shuffles per value, and time-indexed sums are warp-reduced once per
+// t.  The loss gradient can be far below the fp16 range, so everything it multiplies is fp32; only the GELU'
+// evaluations are packed fp16.
 template <typename TIn, int C, int CIN, bool kRegs>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (CIN == 1 ? 4 : 2))      // several input channels: more live values, no spills
 lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const float* __restrict__ b1,
                 const float* __restrict__ W2, const float* __restrict__ b2,
                 const __nv_bfloat16* __restrict__ dh, float* __restrict__ gW1, float* __restrict__ gb1,
                 float* __restrict__ gW2, float* __restrict__ gb2, LiftDims d) {
+  static_assert(C % 4 == 0, "the channels are split over four lanes");
+  constexpr int CG = C / 4;
   __shared__ float sw[kLiftMaxW];
   __shared__ float sg[kLiftMaxW];
   float* sW1 = sw;
@@ -159,21 +164,23 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
   for (int i = threadIdx.x; i < C; i += blockDim.x) sb2[i] = __float2half2_rn(b2[i]);
   __syncthreads();
 
-  float accb2[C], accW2[C][CIN];
+  float accb2[CG], accW2[CG][CIN];
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    accb2[c] = 0.f;
+  for (int u = 0; u < CG; ++u) {
+    accb2[u] = 0.f;
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) accW2[c][ci] = 0.f;
+    for (int ci = 0; ci < CIN; ++ci) accW2[u][ci] = 0.f;
   }
   const int lane = threadIdx.x & 31;
+  const int cg = lane & 3, c0 = cg * CG;                     // this lane's channels: [c0, c0 + CG)
   const int zv = d.Z >> 3;
   const long long plane = static_cast<long long>(d.X) * d.Y;
   const long long nitems = static_cast<long long>(d.B) * plane * zv;
-  const long long per_it = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long per_it = (static_cast<long long>(gridDim.x) * blockDim.x) >> 2;
   const long long nloop = (nitems + per_it - 1) / per_it;
+  const long long item0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 2;
   for (long long it = 0; it < nloop; ++it) {
-    const long long idx = it * per_it + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long idx = it * per_it + item0;
     const bool ok = idx < nitems;                           // whole warps stay in the loop (shuffles)
     const long long id = ok ? idx : 0;
     const int z0 = static_cast<int>(id % zv) * 8;
@@ -186,8 +193,8 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) lift_load8<TIn>(xb + ci * xci_stride, 1, 0, xr[ci]);
     }
-    const __nv_bfloat16* gb = dh + ((static_cast<long long>(b) * C * plane + xy) * d.T) * d.Z + z0;
     const long long hc_stride = plane * d.T * d.Z;
+    const __nv_bfloat16* gb = dh + ((static_cast<long long>(b) * C * plane + xy) * d.T) * d.Z + z0 + c0 * hc_stride;
     for (int t = 0; t < d.T; ++t) {
       __half2 a1[CIN][4];
       float a1f[CIN][8], g1f[CIN][8], da1[CIN][8];
@@ -205,45 +212,53 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
           da1[ci][2 * k] = 0.f; da1[ci][2 * k + 1] = 0.f;
         }
       }
-      static_assert(C % 4 == 0, "channels are processed four at a time");
+      uint4 gv[CG];                                         // this lane's channel loads, all in flight together
 #pragma unroll
-      for (int c4 = 0; c4 < C; c4 += 4) {
-        uint4 gv[4];                                        // four channel loads in flight together
+      for (int u = 0; u < CG; ++u)
+        gv[u] = ok ? *reinterpret_cast<const uint4*>(gb + u * hc_stride + static_cast<long long>(t) * d.Z)
+                   : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          gv[u] = ok ? *reinterpret_cast<const uint4*>(gb + (c4 + u) * hc_stride + static_cast<long long>(t) * d.Z)
-                     : make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < CG; ++u) {
+        const int c = c0 + u;
+        const uint32_t gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+        float dv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = c4 + u;
-          const uint32_t gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
-          float dv[8];
+        for (int k = 0; k < 4; ++k) {
+          __half2 acc = sb2[c];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            __half2 acc = sb2[c];
+          for (int ci = 0; ci < CIN; ++ci) acc = __hfma2(sW2[c * CIN + ci], a1[ci][k], acc);
+          const float2 gr = __half22float2(gelu_vg_h2(acc).grad);
+          const float2 g = unpack_bf16x2(gw[k]);
+          dv[2 * k] = g.x * gr.x; dv[2 * k + 1] = g.y * gr.y;
+        }
+        float sb = 0.f;
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) acc = __hfma2(sW2[c * CIN + ci], a1[ci][k], acc);
-            const float2 gr = __half22float2(gelu_vg_h2(acc).grad);
-            const float2 g = unpack_bf16x2(gw[k]);
-            dv[2 * k] = g.x * gr.x; dv[2 * k + 1] = g.y * gr.y;
+        for (int z = 0; z < 8; ++z) sb += dv[z];
+        accb2[u] += sb;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float w = sW2f[c * CIN + ci];
+          float sacc = 0.f;
+#pragma unroll
+          for (int z = 0; z < 8; ++z) {
+            sacc = fmaf(dv[z], a1f[ci][z], sacc);
+            da1[ci][z] = fmaf(w, dv[z], da1[ci][z]);
           }
-          float sb = 0.f;
-#pragma unroll
-          for (int z = 0; z < 8; ++z) sb += dv[z];
-          accb2[c] += sb;
-#pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) {
-            const float w = sW2f[c * CIN + ci];
-            float sacc = 0.f;
-#pragma unroll
-            for (int z = 0; z < 8; ++z) {
-              sacc = fmaf(dv[z], a1f[ci][z], sacc);
-              da1[ci][z] = fmaf(w, dv[z], da1[ci][z]);
-            }
-            accW2[c][ci] += sacc;
-          }
+          accW2[u][ci] += sacc;
         }
       }
+      // input-gradient partials of the four channel quarters -> every lane of the quad holds the full sum
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int z = 0; z < 8; ++z) {
+          float v = da1[ci][z];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          da1[ci][z] = v;
+        }
+      }
+      const bool own = ok && cg == 0;                       // one lane of the quad feeds the time-indexed sums
       float sb1v = 0.f;
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
@@ -261,25 +276,32 @@ lift_bwd_kernel(const TIn* __restrict__ x, const float* __restrict__ W1, const f
           float sres = 0.f;
 #pragma unroll
           for (int z = 0; z < 8; ++z) sres = fmaf(e[z], xv[z], sres);
-          sres = warp_sum(ok ? sres : 0.f);
+          sres = warp_sum(own ? sres : 0.f);
           if (lane == 0) atomicAdd(&gsW1[t * d.Tin + ti], sres);
         }
       }
-      sb1v = warp_sum(ok ? sb1v : 0.f);
+      sb1v = warp_sum(own ? sb1v : 0.f);
       if (lane == 0) atomicAdd(&gsb1[t], sb1v);
     }
   }
   __shared__ float gsW2[64 * 4 + 64];
   for (int i = threadIdx.x; i < C * CIN + C; i += blockDim.x) gsW2[i] = 0.f;
   __syncthreads();
+  // channel sums: lanes with the same quarter (lane & 3) hold partials of the same channels
+  auto quarter_sum = [](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+  };
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float sres = warp_sum(accb2[c]);
-    if (lane == 0) atomicAdd(&gsW2[C * CIN + c], sres);
+  for (int u = 0; u < CG; ++u) {
+    const float sres = quarter_sum(accb2[u]);
+    if (lane < 4) atomicAdd(&gsW2[C * CIN + c0 + u], sres);
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
-      const float sw2 = warp_sum(accW2[c][ci]);
-      if (lane == 0) atomicAdd(&gsW2[c * CIN + ci], sw2);
+      const float sw2 = quarter_sum(accW2[u][ci]);
+      if (lane < 4) atomicAdd(&gsW2[(c0 + u) * CIN + ci], sw2);
     }
   }
   __syncthreads();
@@ -613,7 +635,7 @@ const char* lift_bwd(const void* x, int x_is_bf16, const float* W1, const float*
                      LiftDims d, int num_sms, cudaStream_t s) {
   if (const char* e = lift_check(d)) return e;
   const long long nitems = static_cast<long long>(d.B) * d.X * d.Y * (d.Z / 8);
-  const int grid = grid_for(nitems, 128, num_sms, 4);
+  const int grid = grid_for(4 * nitems, 128, num_sms, 4);          // four lanes per item (channel quarters)
   const bool regs = d.Tin == 1;
   const char* err = nullptr;
   DFNO_DISPATCH_C(d.C, (err = lift_bwd_cin<kC>(x, x_is_bf16, W1, b1, W2, b2, dh, gW1, gb1, gW2, gb2, d, grid, regs, s)));

@@ -228,3 +228,30 @@ def test_permute_u32_matches_torch_permute():
         C.permute_u32(b.view(-1), outb.view(-1), size, sstr, dstr)
         torch.cuda.synchronize()
         assert torch.equal(outb, wantb), inner
+
+
+# ------------------------------------------------------------------------------------------ losses (csrc/loss.cu)
+@pytest.mark.parametrize("shape", [(2, 1, 12, 10, 16, 7), (1, 1, 33, 5, 9), (3, 2, 1031)])
+def test_native_losses_match_the_autograd_formulation(shape):
+    import dfno_b200 as d
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(3)
+    P = d.Partition([0], [1] * len(shape))
+    y = torch.randn(*shape, device=dev, generator=g)
+    yh = (y + 0.3 * torch.randn(*shape, device=dev, generator=g)).requires_grad_()
+    yh64 = yh.detach().double().requires_grad_()
+    B = shape[0]
+    for crit, ref in ((d.DistributedRelativeLpLoss(P), lambda a, b: ((a - b).reshape(B, -1).norm(dim=1)
+                                                                       / b.reshape(B, -1).norm(dim=1)).mean()),
+                      (d.DistributedMSELoss(P), lambda a, b: ((a - b) ** 2).mean())):
+        assert crit.local
+        yh.grad = None; yh64.grad = None
+        out = crit(yh, y)
+        out.backward()
+        want = ref(yh64, y.double())
+        want.backward()
+        assert abs(float(out) - float(want)) <= 2e-6 * abs(float(want))
+        assert rel(yh.grad, yh64.grad) < 1e-5
+    # non-contiguous / half-precision inputs keep the portable formulation
+    out = d.DistributedRelativeLpLoss(P)(yh.to(torch.bfloat16), y.to(torch.bfloat16))
+    assert torch.isfinite(out)
