@@ -62,7 +62,7 @@ def main():
             peaks["hbm"] = float(j.get("hbm_copy_gbs", j.get("hbm_gbs", peaks["hbm"])))
         except Exception:       # noqa: BLE001 - fall back to the recorded value
             pass
-    cm = pl.cost_model(hbm_gbs=peaks["hbm"], nvlink_gbs=peaks["link"])
+    cm = pl.cost_model(hbm_gbs=peaks["hbm"], nvlink_gbs=peaks["link"], front=True)
     print(f"\ntraffic of one training step per rank: {cm['hbm_bytes'] / 1e9:.2f} GB HBM -> {cm['hbm_floor_ms']:.2f} ms at "
           f"{peaks['hbm']:.0f} GB/s;  {cm['nvlink_bytes'] / 1e6:.0f} MB over NVLink -> {cm['nvlink_ms']:.3f} ms at "
           f"{peaks['link']:.0f} GB/s (overlappable)")

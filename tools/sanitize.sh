@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 CS="compute-sanitizer --tool $tool --error-exitcode 1 --launch-timeout 120 --target-processes all"
 rc=0
 $CS python -m pytest tests/test_dft_gemm_gpu.py tests/test_fused_pointwise_gpu.py tests/test_fft_radix_gpu.py \
-    -x -q -k "rowmajor or scatter or spectral_out or dpre_dw or head or forward_inverse" \
+    tests/test_spectral_in_gpu.py -x -q -k "rowmajor or scatter or spectral_out or dpre_dw or head or forward_inverse or spectral_in" \
     > gpurun_out/sanitize_${tool}.log 2>&1 || rc=$?
 tail -n 5 gpurun_out/sanitize_${tool}.log
 if [ "${N:-1}" -ge 2 ]; then
