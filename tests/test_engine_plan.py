@@ -286,3 +286,41 @@ def test_cost_model_reproduces_measured_dram_traffic():
     c8 = p8.cost_model()
     per_chain = c8["nvlink_bytes"] / (2 * 4)
     assert abs(per_chain - 68.8e6) / 68.8e6 < 0.01        # bytes leaving a rank per spectral convolution
+
+
+def test_fused_front_stage_plan_and_eligibility():
+    """Host-side tile planner of csrc/spectral_in_sm100.cu (no GPU needed): the configurations the engine relies
+    on are accepted with the expected tile shape, and the documented limits are refused with a reason (the engine
+    then keeps the two separate GEMMs)."""
+    from dfno_b200.ops import build
+    C_ = build.load()
+
+    def cfg(P, off, dstr, BC, X, Yl, T, Z, KZ, mt, n1=None, k1=None, n2=None, k2=None):
+        c16 = lambda v: (v + 15) // 16 * 16
+        c64 = lambda v: (v + 63) // 64 * 64
+        a = (n1 or c16(2 * KZ), k1 or c64(Z), n2 or c16(2 * mt), k2 or c64(2 * T), P, off, dstr, BC, X, Yl, T, Z, KZ, mt)
+        why = C_.spectral_in_check(*a)
+        return why, (C_.spectral_in_config(*a) if not why else None)
+
+    # headline, one rank: S1[bc, kz, kt, x, y, ri]; 4 positions per tile, 32-position store chunks, 3 groups
+    Y = 128
+    why, c = cfg(1, 0, [Y * 2, 128 * Y * 2, 10 * 128 * Y * 2, 24 * 10 * 128 * Y * 2], 20, 128, 128, 20, 128, 24, 10)
+    assert why == "" and c[:3] == [4, 32, 3] and c[3] >= 4
+    # headline, rank 5 of 8, staged layout S1s[bc, kz', kt, r_src, x, y_loc, ri]: 16 local y -> 16-position chunks
+    P, Yl, X = 8, 16, 128
+    dstr = [Yl * 2, P * X * Yl * 2, 10 * P * X * Yl * 2, 3 * 10 * P * X * Yl * 2]
+    why, c = cfg(P, 5 * X * Yl * 2, dstr, 20, X, Yl, 20, 128, 24, 10)
+    assert why == "" and c[:2] == [4, 16]
+    # BASELINE config 3 (256^3 x 16 t, width 32, 12 modes, 8 ranks): four K blocks per tile still fit
+    why, c = cfg(8, 0, [32 * 2, 8 * 256 * 32 * 2, 8 * 8 * 256 * 32 * 2, 3 * 8 * 8 * 256 * 32 * 2], 64, 256, 32, 16, 256, 24, 8)
+    assert why == "" and c[0] >= 1 and c[3] >= 2
+    # two-phase default (60 x 60 x 64 x 30) on 4 ranks: 15 local y is not a multiple of 4 -> separate GEMMs
+    why, _ = cfg(4, 0, [15 * 2 + 2, 8, 8, 8], 20, 60, 15, 30, 64, 24, 8)
+    assert "multiple of 4" in why or "multiples of 8" in why
+    # ... and on one rank (60 local y) it is accepted
+    why, c = cfg(1, 0, [60 * 2, 60 * 60 * 2, 8 * 60 * 60 * 2, 24 * 8 * 60 * 60 * 2], 20, 60, 60, 30, 64, 24, 8)
+    assert why == "" and c[0] == 4
+    # documented limits
+    assert "T <= 64" in cfg(1, 0, [256, 256, 256, 256], 4, 4, 32, 80, 64, 8, 4, k2=192)[0]
+    assert "alignment" in cfg(2, 4, [256, 256, 256, 256], 4, 4, 32, 20, 64, 8, 4)[0]           # y offset not 16-byte aligned
+    assert cfg(3, 0, [256, 256, 256, 256], 4, 4, 32, 20, 64, 8, 4)[0] != ""                    # KZ not divisible by the ranks
