@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""spectral_in in isolation at the headline shape, with the probe switches of csrc/spectral_in_sm100.cu
+"""(Needs an extension built with -DDFNO_SPIN_PROBE, e.g. DFNO_EXTRA_NVCC_FLAGS=-DDFNO_SPIN_PROBE; the product build
+ignores the switches and this script then only times the shipped kernel.)
+
+spectral_in in isolation at the headline shape, with the probe switches of csrc/spectral_in_sm100.cu
 (DFNO_SPIN_DBG bits: 1 = no epi-1 body, 2 = no epi-2 body, 4 = no TMA stores, 8 = no proxy fences; DFNO_SPIN_E,
 DFNO_SPIN_ST = epilogue groups / ring stages), against the two dft_gemm launches it replaces."""
 import os, sys

@@ -27,6 +27,14 @@
 namespace dfno {
 namespace {
 
+// Probe switches (benchmarks/spin_probe.py, profiles/r2_spin_probe.txt): parts of the kernel can be turned off at run
+// time to see what paces it.  Compiled in only with -DDFNO_SPIN_PROBE; the product build has none of the branches.
+#ifdef DFNO_SPIN_PROBE
+#define DFNO_SPIN_DBG(p) ((p).dbg)
+#else
+#define DFNO_SPIN_DBG(p) 0
+#endif
+
 constexpr int kMaxPeersIn = 8;
 constexpr int kMaxE = 4;
 constexpr int kMaxStagesIn = 6;
@@ -106,8 +114,8 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t gcols = (p.dbg & 128) ? 128u : static_cast<uint32_t>(p.n1_pad + p.n2_pad);   // TMEM columns per group: [D1 | D2]
-  const uint32_t d2col = (p.dbg & 128) ? 64u : static_cast<uint32_t>(p.n1_pad);
+  const uint32_t gcols = (DFNO_SPIN_DBG(p) & 128) ? 128u : static_cast<uint32_t>(p.n1_pad + p.n2_pad);   // TMEM columns per group: [D1 | D2]
+  const uint32_t d2col = (DFNO_SPIN_DBG(p) & 128) ? 64u : static_cast<uint32_t>(p.n1_pad);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -122,7 +130,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
         for (int tt = 0; tt < p.tpc; ++tt) {
           const int line0 = (cy * p.Yc + tt * p.Rp) * p.T;
           mbar_wait(&empty[s], ph ^ 1);
-          if (p.dbg & 16) { mbar_arrive(&full[s]); if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1; } continue; }
+          if (DFNO_SPIN_DBG(p) & 16) { mbar_arrive(&full[s]); if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1; } continue; }
           mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(p.k1blocks) * p.RT * 128);
           uint8_t* dst = s_ring + s * p.stage_bytes;
           for (int kb = 0; kb < p.k1blocks; ++kb) tma_load_3d(dst + kb * p.blk1, &tmH, &full[s], kb * 64, line0, row);
@@ -191,7 +199,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
         const uint32_t b = cn & 1;
         mbar_wait(&stg_done[b], (cn >> 1) & 1);
         const uint8_t* src = s_stg + b * p.stg_bytes;
-        if (!(p.dbg & 4)) for (int j = 0; j < p.P; ++j) tma_store_5d(&pm.m[j], src + j * p.peer_bytes, cy * p.Yc * 2, x, 0, 0, bc);
+        if (!(DFNO_SPIN_DBG(p) & 4)) for (int j = 0; j < p.P; ++j) tma_store_5d(&pm.m[j], src + j * p.peer_bytes, cy * p.Yc * 2, x, 0, 0, bc);
         tma_store_commit();
         tma_store_wait_read();
         mbar_arrive(&stg_free[b]);
@@ -220,7 +228,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
     uint32_t u = 0, cn = 0;                               // phase parity of this group's barriers; chunk counter
     // one lane polls, the warp follows: 128 threads spinning on try_wait slow every other mbarrier operation down
     auto wait_warp = [&](uint64_t* bar, uint32_t parity) {
-      if (lane == 0) { if (p.dbg & 256) mbar_spin(bar, parity); else mbar_wait(bar, parity); }
+      if (lane == 0) { if (DFNO_SPIN_DBG(p) & 256) mbar_spin(bar, parity); else mbar_wait(bar, parity); }
       __syncwarp();
     };
     for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++cn) {
@@ -232,7 +240,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
         // ---------------- epi-1 ----------------
         wait_warp(&d1_full[g], u);
         tcgen05_fence_after();
-        if (warp1 && !(p.dbg & 1)) {
+        if (warp1 && !(DFNO_SPIN_DBG(p) & 1)) {
           for (int c0 = 0; c0 < n1; c0 += 16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + c0, v);
@@ -251,7 +259,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
           }
         }
         tcgen05_fence_before();
-        if (!(p.dbg & 8)) fence_proxy_async_smem();
+        if (!(DFNO_SPIN_DBG(p) & 8)) fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
         if (elected) { mbar_arrive(&d1_empty[g]); mbar_arrive(&a2_full[g]); }
         // ---------------- epi-2 ----------------
@@ -259,7 +267,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
         tcgen05_fence_after();
         wait_warp(&stg_free[cn & 1], ((cn >> 1) & 1) ^ 1);
         u ^= 1;
-        if (warp2 && !(p.dbg & 2)) {
+        if (warp2 && !(DFNO_SPIN_DBG(p) & 2)) {
           for (int c0 = 0; c0 < n2; c0 += 16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + d2col + c0, v);
@@ -276,7 +284,7 @@ spectral_in_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constan
           }
         }
         tcgen05_fence_before();
-        if (!(p.dbg & 8)) fence_proxy_async_smem();
+        if (!(DFNO_SPIN_DBG(p) & 8)) fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
         if (elected) mbar_arrive(&stg_done[cn & 1]);
       }
@@ -369,9 +377,11 @@ const char* spectral_in(const void* h, const void* op1, int n1_pad, int k1_pad, 
                         int Yl, int T, int Z, int KZ, int mt, int num_sms, cudaStream_t stream) {
   SpecInParams p;
   if (const char* err = plan_spectral_in(p, n1_pad, k1_pad, n2_pad, k2_pad, P, dst_off, dstr, BC, X, Yl, T, Z, KZ, mt)) return err;
-  if (const char* e = getenv("DFNO_SPIN_DBG")) p.dbg = atoi(e);            // probe switches (benchmarks/spin_probe.py)
-  if (const char* e = getenv("DFNO_SPIN_E")) { const int v = atoi(e); if (v >= 1 && v <= kMaxE && v * (n1_pad + n2_pad) <= 512) p.E = v; }
+#ifdef DFNO_SPIN_PROBE
+  if (const char* e = getenv("DFNO_SPIN_DBG")) p.dbg = atoi(e);
+  if (const char* e = getenv("DFNO_SPIN_E")) { const int v = atoi(e); if (v >= 1 && v <= 3 && v * (n1_pad + n2_pad) <= 512) p.E = v; }
   if (const char* e = getenv("DFNO_SPIN_ST")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStagesIn) p.stages = v; }
+#endif
   const uint32_t ops_bytes = static_cast<uint32_t>(p.k1blocks) * n1_pad * 128 + static_cast<uint32_t>(p.k2blocks) * n2_pad * 128;
   CUtensorMap tmH, tmB1, tmB2;
   PeerMaps pm;

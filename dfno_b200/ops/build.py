@@ -21,7 +21,7 @@ NAME = "dfno_b200_C"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xptxas", "-v",
-]
+] + os.environ.get("DFNO_EXTRA_NVCC_FLAGS", "").split()        # e.g. -DDFNO_SPIN_PROBE for benchmarks/spin_probe.py
 BUILD_DIR = os.path.normpath(os.path.join(_HERE, "..", "_build"))
 
 _lock = threading.Lock()
