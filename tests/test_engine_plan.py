@@ -324,3 +324,64 @@ def test_fused_front_stage_plan_and_eligibility():
     assert "T <= 64" in cfg(1, 0, [256, 256, 256, 256], 4, 4, 32, 80, 64, 8, 4, k2=192)[0]
     assert "alignment" in cfg(2, 4, [256, 256, 256, 256], 4, 4, 32, 20, 64, 8, 4)[0]           # y offset not 16-byte aligned
     assert cfg(3, 0, [256, 256, 256, 256], 4, 4, 32, 20, 64, 8, 4)[0] != ""                    # KZ not divisible by the ranks
+
+
+def _emulate_spectral_in(h, o1, o2, dst, dst_off, dstr, BC, X, Yl, T, Z, KZ, mt, P, Rp, Yc):
+    """Float64 replay of csrc/spectral_in_sm100.cu with the kernel's own index arithmetic: tiles of Rp positions,
+    D1 -> A2 transposition, D2 -> staging[kz][kt][y], one clipped box store per destination rank and chunk."""
+    kzl, tpc, ncy = KZ // P, Yc // Rp, (Yl + Yc - 1) // Yc
+    lines = h.reshape(BC * X, Yl * T, Z)
+    for row in range(BC * X):
+        bc, x = divmod(row, X)
+        for cy in range(ncy):
+            stg = torch.zeros(KZ * mt * Yc, 2, dtype=torch.float64)
+            for tt in range(tpc):
+                line0 = (cy * Yc + tt * Rp) * T
+                tile = torch.zeros(Rp * T, Z, dtype=torch.float64)          # TMA box: rows past the tensor are zero
+                n = max(0, min(Rp * T, Yl * T - line0))
+                tile[:n] = lines[row, line0:line0 + n]
+                D1 = tile @ o1.t()                                          # [m1 = p*T + t, 2 kz + ri]
+                A2 = torch.zeros(KZ * Rp, 2 * T, dtype=torch.float64)
+                for m1 in range(Rp * T):
+                    p1, t1 = divmod(m1, T)
+                    for kz in range(KZ):
+                        A2[kz * Rp + p1, 2 * t1:2 * t1 + 2] = D1[m1, 2 * kz:2 * kz + 2]
+                D2 = A2 @ o2.t()                                            # [m2 = kz*Rp + p, 2 kt + ri]
+                for m2 in range(KZ * Rp):
+                    kz2, p2 = divmod(m2, Rp)
+                    for kt in range(mt):
+                        stg[(kz2 * mt + kt) * Yc + tt * Rp + p2] = D2[m2, 2 * kt:2 * kt + 2]
+            box = stg.view(KZ, mt, Yc, 2)
+            ny = max(0, min(Yc, Yl - cy * Yc))                              # the store is clipped at the row end
+            for j in range(P):
+                for kzp in range(kzl):
+                    for kt in range(mt):
+                        base = dst_off + bc * dstr[3] + kzp * dstr[2] + kt * dstr[1] + x * dstr[0] + cy * Yc * 2
+                        dst[j][base:base + 2 * ny] = box[j * kzl + kzp, kt, :ny].reshape(-1)
+
+
+@pytest.mark.parametrize("P,staged,Yl,Rp,Yc", [(1, False, 8, 4, 8), (2, False, 8, 2, 4), (4, True, 12, 4, 8)])
+def test_fused_front_stage_dataflow_emulated(P, staged, Yl, Rp, Yc):
+    from dfno_b200.ops import operators as OPS
+    torch.manual_seed(0)
+    BC, X, T, Z, mz, mt, r = 2, 3, 6, 8, 2, 2, P - 1
+    KZ, kzl, Y = 2 * mz, 2 * mz // P, Yl * P
+    o1, o2 = OPS.fwd_real_to_complex(Z, mz), OPS.fwd_complex(T, mt, False)
+    h = torch.randn(BC, X, Yl, T, Z, dtype=torch.float64)
+    if staged:      # S1s[bc, kz', kt, r_src, x, y_loc, ri] on the owner of kz
+        dstr, off, n = [Yl * 2, P * X * Yl * 2, mt * P * X * Yl * 2, kzl * mt * P * X * Yl * 2], r * X * Yl * 2, BC * kzl * mt * P * X * Yl * 2
+    else:           # S1[bc, kz', kt, x, y, ri]
+        dstr, off, n = [Y * 2, X * Y * 2, mt * X * Y * 2, kzl * mt * X * Y * 2], r * Yl * 2, BC * kzl * mt * X * Y * 2
+    dst = [torch.full((n,), float("nan"), dtype=torch.float64) for _ in range(P)]
+    _emulate_spectral_in(h, o1, o2, dst, off, dstr, BC, X, Yl, T, Z, KZ, mt, P, Rp, Yc)
+    z1 = (h.reshape(-1, Z) @ o1.t()).view(BC * X * Yl, T, KZ, 2).permute(0, 2, 1, 3).reshape(-1, 2 * T)
+    ref = (z1 @ o2.t()).view(BC, X, Yl, KZ, mt, 2).permute(0, 3, 4, 1, 2, 5)       # [bc, kz, kt, x, y, ri]
+    for j in range(P):
+        if staged:
+            got = dst[j].view(BC, kzl, mt, P, X, Yl, 2)
+            mine, rest = got[:, :, :, r], torch.cat([got[:, :, :, :r], got[:, :, :, r + 1:]], 3)
+        else:
+            got = dst[j].view(BC, kzl, mt, X, Y, 2)
+            mine, rest = got[..., r * Yl:(r + 1) * Yl, :], torch.cat([got[..., :r * Yl, :], got[..., (r + 1) * Yl:, :]], -2)
+        assert torch.allclose(mine, ref[:, j * kzl:(j + 1) * kzl], atol=1e-12)
+        assert torch.isnan(rest).all()                  # nothing outside this rank's slice of the destination is written
