@@ -334,8 +334,8 @@ const char* plan_spectral_in(SpecInParams& p, int n1_pad, int k1_pad, int n2_pad
       const uint32_t blk1 = align_up_u32(static_cast<uint32_t>(Rp) * T * 128, 1024);
       const uint32_t a2blk = align_up_u32(static_cast<uint32_t>(Rp) * KZ * 128, 1024);
       const uint32_t n_g = static_cast<uint32_t>(n1_pad + n2_pad);
-      static const int tryE[] = {3, 2, 1};
-      for (int ie = 0; ie < 3 && !ok; ++ie) {
+      static const int tryE[] = {4, 3, 2, 1};
+      for (int ie = 0; ie < 4 && !ok; ++ie) {
         const int E = tryE[ie];
         if (E * n_g > 512) continue;
         for (int st = 5; st >= 2; --st) {

@@ -302,10 +302,10 @@ def test_fused_front_stage_plan_and_eligibility():
         why = C_.spectral_in_check(*a)
         return why, (C_.spectral_in_config(*a) if not why else None)
 
-    # headline, one rank: S1[bc, kz, kt, x, y, ri]; 4 positions per tile, 32-position store chunks, 3 groups
+    # headline, one rank: S1[bc, kz, kt, x, y, ri]; 4 positions per tile, 32-position store chunks, 4 groups
     Y = 128
     why, c = cfg(1, 0, [Y * 2, 128 * Y * 2, 10 * 128 * Y * 2, 24 * 10 * 128 * Y * 2], 20, 128, 128, 20, 128, 24, 10)
-    assert why == "" and c[:3] == [4, 32, 3] and c[3] >= 4
+    assert why == "" and c[:3] == [4, 32, 4] and c[3] >= 4
     # headline, rank 5 of 8, staged layout S1s[bc, kz', kt, r_src, x, y_loc, ri]: 16 local y -> 16-position chunks
     P, Yl, X = 8, 16, 128
     dstr = [Yl * 2, P * X * Yl * 2, 10 * P * X * Yl * 2, 3 * 10 * P * X * Yl * 2]
