@@ -6,8 +6,8 @@
 //
 // p = one (x, y) position of one (batch, channel) row, Rp positions per tile.  The round-2 chain ran the two
 // GEMMs as separate launches with Z1 (0.63 GB per pass at 128^3 x 20) written to and re-read from HBM, and the
-// second one -- K = 2T = 40, 80-byte operand rows -- bound by TMA row requests at 0.44 of copy bandwidth.  Here
-// Z1 never leaves the SM:
+// second one -- K = 2T = 40, 80-byte operand rows -- running at 0.44 of copy bandwidth.  Here Z1 never leaves the
+// SM:
 //
 //   MMA1   D1[m1 = p*T + t, n = 2 kz + ri]   A1 = the h tile (TMA, Rp*T lines of Z samples, K-major), B1 = F1
 //   epi-1  D1 -> bf16 -> A2[m2 = kz*Rp + p, k = 2 t + ri]   (TMEM -> registers -> swizzled shared memory: the
